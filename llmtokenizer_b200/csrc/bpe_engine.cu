@@ -1,0 +1,1083 @@
+// Host side of the B200 BPE merge-loop engine + the C ABI of include/bpe_cuda.h.
+//
+// One context per GPU.  A merge step is a fixed sequence of launches driven entirely by a
+// device-resident control block (bpe::DevState): select -> replace(+scan+deltas) -> [edge record,
+// ncclAllReduce] -> apply.  The host enqueues steps in batches and polls the control block once
+// per batch (stop / pause / table occupancy), so there is no host round trip per merge.
+//
+// There is no CPU fallback anywhere in this file: without a CUDA device every entry point fails.
+#include "../../include/bpe_cuda.h"
+#include "bpe_kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace bpe;
+
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static char g_err_global[512] = "";
+
+static void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    memcpy(g_err_global, g_err, sizeof g_err);
+}
+
+#define CU(call)                                                                                                       \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t e_ = (call);                                                                                       \
+        if (e_ != cudaSuccess)                                                                                         \
+        {                                                                                                              \
+            set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call);               \
+            return BPE_CUDA_ERR_CUDA;                                                                                  \
+        }                                                                                                              \
+    } while (0)
+
+// NCCL is resolved at run time (dlopen) so that the single-GPU path carries no link dependency.
+struct NcclApi
+{
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load()
+{
+    if (g_nccl.lib)
+        return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *nm : names)
+        if ((h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL)))
+            break;
+    if (!h)
+    {
+        set_error("cannot load NCCL: %s", dlerror());
+        return BPE_CUDA_ERR_CUDA;
+    }
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.AllGather || !g_nccl.CommDestroy)
+    {
+        set_error("NCCL library lacks required symbols");
+        return BPE_CUDA_ERR_CUDA;
+    }
+    g_nccl.lib = h;
+    return 0;
+}
+
+#define NC(call)                                                                                                       \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        ncclResult_t r_ = (call);                                                                                      \
+        if (r_ != ncclSuccess)                                                                                         \
+        {                                                                                                              \
+            set_error("NCCL error %s at %s:%d", g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?", __FILE__,     \
+                      __LINE__);                                                                                       \
+            return BPE_CUDA_ERR_CUDA;                                                                                  \
+        }                                                                                                              \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+struct bpe_cuda_ctx
+{
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    // resident input shard
+    uint8_t *d_bytes = nullptr;
+    size_t bytes_cap = 0, n_bytes = 0;
+    // token stream ping-pong
+    u32 *d_tok_alloc[2] = {nullptr, nullptr};
+    size_t tok_cap = 0;
+    // control block
+    DevState *d_st = nullptr;
+    DevState *h_st = nullptr; // pinned
+    // tile descriptors
+    u64 *d_desc = nullptr;
+    u32 *d_pdesc = nullptr;
+    size_t desc_cap = 0;
+    // delta vectors (+ edge-record header)
+    int32_t *d_delta = nullptr, *d_delta_red = nullptr;
+    size_t delta_cap = 0;
+    // pair table
+    u64 *d_tkey = nullptr, *d_tmeta = nullptr;
+    u64 tcap = 0;
+    // logs
+    u32 *d_merges = nullptr;
+    u64 *d_nhist = nullptr;
+    size_t merges_cap = 0;
+    u32 *d_enc_merges = nullptr;
+    size_t enc_cap = 0;
+    // selection partials / dense byte-pair histogram
+    SelPart *d_part = nullptr;
+    int sel_grid = 0;
+    u32 *d_dense = nullptr;
+    // communicator
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    // options
+    int profile_replace = 0;
+    int batch_steps = 64;
+    int smem_hist_max_vocab = 2048;
+    int force_census = 0;
+    int replace_occ[2] = {0, 0};
+    // profiling events
+    std::vector<cudaEvent_t> prof;
+    size_t prof_used = 0;
+    // results
+    size_t res_n_merges = 0, res_n_tokens = 0;
+    bpe_cuda_stats_t stats;
+    uint64_t launches = 0;
+};
+
+static inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+static int ensure_bytes(bpe_cuda_ctx *c, size_t n)
+{
+    const size_t need = round_up(n, 16) + 64;
+    if (need > c->bytes_cap)
+    {
+        if (c->d_bytes)
+            CU(cudaFree(c->d_bytes));
+        c->d_bytes = nullptr;
+        CU(cudaMalloc(&c->d_bytes, need));
+        c->bytes_cap = need;
+    }
+    return 0;
+}
+
+static int ensure_stream_buffers(bpe_cuda_ctx *c, size_t n)
+{
+    const size_t need = round_up(n, 16) + 64; // 4 slots in front, slack behind for whole-vector stores
+    if (need > c->tok_cap)
+    {
+        for (int i = 0; i < 2; i++)
+        {
+            if (c->d_tok_alloc[i])
+                CU(cudaFree(c->d_tok_alloc[i]));
+            c->d_tok_alloc[i] = nullptr;
+            CU(cudaMalloc(&c->d_tok_alloc[i], need * sizeof(u32)));
+        }
+        c->tok_cap = need;
+    }
+    const size_t tiles = n / R_TILE + 2;
+    if (tiles > c->desc_cap)
+    {
+        if (c->d_desc)
+            CU(cudaFree(c->d_desc));
+        if (c->d_pdesc)
+            CU(cudaFree(c->d_pdesc));
+        c->d_desc = nullptr;
+        c->d_pdesc = nullptr;
+        CU(cudaMalloc(&c->d_desc, tiles * sizeof(u64)));
+        CU(cudaMalloc(&c->d_pdesc, tiles * sizeof(u32)));
+        c->desc_cap = tiles;
+    }
+    return 0;
+}
+
+static int ensure_delta(bpe_cuda_ctx *c, size_t vocab)
+{
+    const size_t need = HDR_INTS + 4 * (vocab + 1);
+    if (need <= c->delta_cap)
+        return 0;
+    size_t cap = c->delta_cap ? c->delta_cap : (size_t)HDR_INTS + 4 * 8192;
+    while (cap < need)
+        cap *= 2;
+    // the vectors are all-zero between steps and the stream is idle when this is called; the
+    // header (edge records) must survive
+    int32_t *nd = nullptr, *nr = nullptr;
+    CU(cudaMalloc(&nd, cap * sizeof(int32_t)));
+    CU(cudaMemsetAsync(nd, 0, cap * sizeof(int32_t), c->stream));
+    if (c->d_delta)
+        CU(cudaMemcpyAsync(nd, c->d_delta, HDR_INTS * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+    if (c->world > 1)
+    {
+        CU(cudaMalloc(&nr, cap * sizeof(int32_t)));
+        CU(cudaMemsetAsync(nr, 0, cap * sizeof(int32_t), c->stream));
+        if (c->d_delta_red)
+            CU(cudaMemcpyAsync(nr, c->d_delta_red, HDR_INTS * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->d_delta)
+        CU(cudaFree(c->d_delta));
+    if (c->d_delta_red && c->d_delta_red != c->d_delta)
+        CU(cudaFree(c->d_delta_red));
+    c->d_delta = nd;
+    c->d_delta_red = (c->world > 1) ? nr : nd;
+    c->delta_cap = cap;
+    return 0;
+}
+
+static int ensure_logs(bpe_cuda_ctx *c, size_t merges)
+{
+    if (merges <= c->merges_cap)
+        return 0;
+    size_t cap = c->merges_cap ? c->merges_cap : 8192;
+    while (cap < merges)
+        cap *= 2;
+    u32 *nm = nullptr;
+    u64 *nh = nullptr;
+    CU(cudaMalloc(&nm, cap * 2 * sizeof(u32)));
+    CU(cudaMalloc(&nh, (cap + 1) * sizeof(u64)));
+    if (c->d_merges)
+    {
+        CU(cudaMemcpyAsync(nm, c->d_merges, c->merges_cap * 2 * sizeof(u32), cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(nh, c->d_nhist, (c->merges_cap + 1) * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaFree(c->d_merges));
+        CU(cudaFree(c->d_nhist));
+    }
+    c->d_merges = nm;
+    c->d_nhist = nh;
+    c->merges_cap = cap;
+    // the control block holds the pointers
+    CU(cudaMemcpyAsync(&c->d_st->merges, &c->d_merges, sizeof(u32 *), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(&c->d_st->n_hist, &c->d_nhist, sizeof(u64 *), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int table_alloc(bpe_cuda_ctx *c, u64 cap, u64 **key, u64 **meta)
+{
+    CU(cudaMalloc(key, cap * sizeof(u64)));
+    CU(cudaMalloc(meta, cap * sizeof(u64)));
+    CU(cudaMemsetAsync(*key, 0xFF, cap * sizeof(u64), c->stream));
+    CU(cudaMemsetAsync(*meta, 0, cap * sizeof(u64), c->stream));
+    return 0;
+}
+
+static int table_rehash(bpe_cuda_ctx *c, u64 new_cap)
+{
+    u64 *nk = nullptr, *nm = nullptr;
+    int rc = table_alloc(c, new_cap, &nk, &nm);
+    if (rc)
+        return rc;
+    const int grid = (int)std::min<u64>((c->tcap + 255) / 256, (u64)c->sm_count * 8);
+    rehash_kernel<<<grid, 256, 0, c->stream>>>(c->d_tkey, c->d_tmeta, c->tcap, nk, nm, new_cap, &c->d_st->err);
+    table_swap_kernel<<<1, 1, 0, c->stream>>>(c->d_st, nk, nm, new_cap);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(c->d_tkey));
+    CU(cudaFree(c->d_tmeta));
+    c->d_tkey = nk;
+    c->d_tmeta = nm;
+    c->tcap = new_cap;
+    c->stats.table_rehashes++;
+    return 0;
+}
+
+static int poll_state(bpe_cuda_ctx *c)
+{
+    CU(cudaMemcpyAsync(c->h_st, c->d_st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (getenv("BPE_CUDA_DEBUG"))
+        fprintf(stderr, "[bpe_cuda r%d] merges=%llu n=%llu n_global=%llu D=%lld occ=%llu cap=%llu stop=%u pause=%u static=%u err=%u a=%u b=%u f=%u mult=%u\n",
+                c->rank, c->h_st->merges_done, c->h_st->n, c->h_st->n_global, c->h_st->distinct, c->h_st->occupied, c->h_st->tcap,
+                c->h_st->stop, c->h_st->pause, c->h_st->static_mode, c->h_st->err, c->h_st->a, c->h_st->b, c->h_st->freq,
+                c->h_st->sel_mult);
+    if (c->h_st->err)
+    {
+        set_error("device reported error flags 0x%x (1=table full 2=missing key 4=negative count)", c->h_st->err);
+        return BPE_CUDA_ERR_STATE;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+static size_t replace_smem_bytes(bool hist, u32 z) { return (R_TILE + 8) * sizeof(u32) + (hist ? 16 * ((size_t)z + 1) : 0); }
+
+static int setup_kernels(bpe_cuda_ctx *c)
+{
+    CU(cudaFuncSetAttribute(replace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(replace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CU(cudaFuncSetAttribute(widen_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, replace_kernel<false>, R_THREADS, replace_smem_bytes(false, 0)));
+    c->replace_occ[0] = std::max(1, occ);
+    return 0;
+}
+
+// enqueue one merge step; z is the id the step will create if it runs
+static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool with_select)
+{
+    if (with_select)
+    {
+        if (encode)
+            select_rank_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_delta_red);
+        else
+            select_kernel<<<c->sel_grid, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_part, c->d_delta_red);
+        c->launches++;
+    }
+    const bool hist = ((int)z + 1 <= c->smem_hist_max_vocab);
+    const size_t smem = replace_smem_bytes(hist, z);
+    int occ = c->replace_occ[0];
+    if (hist)
+    {
+        const size_t per_sm = 220 * 1024;
+        occ = (int)std::max<size_t>(1, std::min<size_t>((size_t)occ, per_sm / (smem + 1024)));
+    }
+    const u64 tiles = std::max<u64>(1, (n_upper + R_TILE - 1) / R_TILE);
+    const int grid = (int)std::min<u64>(tiles, (u64)c->sm_count * (u64)occ);
+    const bool prof = c->profile_replace && c->prof_used + 2 <= c->prof.size();
+    if (prof)
+        CU(cudaEventRecord(c->prof[c->prof_used++], c->stream));
+    if (hist)
+        replace_kernel<true><<<grid, R_THREADS, smem, c->stream>>>(c->d_st, c->d_desc, c->d_pdesc, c->d_delta);
+    else
+        replace_kernel<false><<<grid, R_THREADS, smem, c->stream>>>(c->d_st, c->d_desc, c->d_pdesc, c->d_delta);
+    if (prof)
+        CU(cudaEventRecord(c->prof[c->prof_used++], c->stream));
+    c->launches++;
+    c->stats.replace_launches++;
+    if (c->world > 1)
+    {
+        edge_record_kernel<<<1, 32, 0, c->stream>>>(c->d_st, c->d_delta, 1);
+        c->launches++;
+        NC(g_nccl.AllReduce(c->d_delta, c->d_delta_red, HDR_INTS + 4 * ((size_t)z + 1), ncclInt32, ncclSum, c->comm,
+                            c->stream));
+    }
+    const int agrid = (int)std::min<u64>((4ull * (z + 1) + 255) / 256, (u64)c->sm_count * 4);
+    apply_kernel<<<agrid, 256, 0, c->stream>>>(c->d_st, c->d_delta_red, c->d_delta);
+    c->launches++;
+    return 0;
+}
+
+// Same-bucket ties / exact-threshold iterations.  (The exact chain-order resolver is launched
+// here; see resolver kernels.)
+static int resolve_pause(bpe_cuda_ctx *c, bool encode);
+
+static int run_loop(bpe_cuda_ctx *c, bool encode)
+{
+    int rc;
+    if ((rc = poll_state(c)))
+        return rc;
+    for (;;)
+    {
+        DevState *h = c->h_st;
+        if (h->stop == STOP_DONE)
+            break;
+        if (h->stop == STOP_PAUSE)
+        {
+            if ((rc = resolve_pause(c, encode)))
+                return rc;
+            if ((rc = poll_state(c)))
+                return rc;
+            continue;
+        }
+        const u64 m0 = h->merges_done;
+        const u64 z0 = 256 + m0;
+        // batch size: bounded by the table headroom it may consume (<= 2*(V+1) new keys a step)
+        u64 G = (u64)std::max(1, c->batch_steps);
+        if (!encode && h->max_merges != ~0ull && h->max_merges >= m0)
+            G = std::min<u64>(G, h->max_merges - m0 + 1);
+        if (encode)
+            G = std::min<u64>(G, h->enc_total - m0 + 1);
+        while (G > 4 && G * 2 * (z0 + G + 1) > c->tcap / 4)
+            G /= 2;
+        const u64 margin = G * 2 * (z0 + G + 1);
+        if (h->occupied + margin > c->tcap / 2 + c->tcap / 8)
+        {
+            u64 want = 1ull << 20;
+            while (want < 4 * ((u64)h->distinct + margin))
+                want *= 2;
+            if ((rc = table_rehash(c, want)))
+                return rc;
+        }
+        if ((rc = ensure_delta(c, (size_t)(z0 + G + 1))))
+            return rc;
+        if ((rc = ensure_logs(c, (size_t)(m0 + G + 1))))
+            return rc;
+        for (u64 g = 0; g < G; g++)
+            if ((rc = enqueue_step(c, (u32)(z0 + g), h->n, encode, true)))
+                return rc;
+        CU(cudaGetLastError());
+        if ((rc = poll_state(c)))
+            return rc;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int init_state(bpe_cuda_ctx *c, u64 n_local, u64 max_merges, bool encode, size_t enc_total)
+{
+    DevState s;
+    memset(&s, 0, sizeof s);
+    s.tok[0] = c->d_tok_alloc[0] + 4;
+    s.tok[1] = c->d_tok_alloc[1] + 4;
+    s.cur = 0;
+    s.epoch = 1;
+    s.n = n_local;
+    s.n_global = n_local;
+    s.max_merges = max_merges ? max_merges : ~0ull;
+    s.tkey = c->d_tkey;
+    s.tmeta = c->d_tmeta;
+    s.tcap = c->tcap;
+    s.halo_before[0] = s.halo_before[1] = SENT;
+    s.halo_after[0] = s.halo_after[1] = s.halo_after[2] = SENT;
+    s.rank = (u32)c->rank;
+    s.world = (u32)c->world;
+    for (int t = 0; t < REF_THREADS; t++)
+        s.bt[t] = 256; // bpe.c:610,615
+    s.merges = c->d_merges;
+    s.n_hist = c->d_nhist;
+    s.enc_merges = c->d_enc_merges;
+    s.enc_total = enc_total;
+    s.static_mode = 0;
+    (void)encode;
+    CU(cudaMemcpyAsync(c->d_st, &s, sizeof s, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_merges, size_t n_enc, bool encode,
+                      bpe_cuda_stats_t *stats_out)
+{
+    int rc;
+    CU(cudaSetDevice(c->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    memset(&c->stats, 0, sizeof c->stats);
+    c->launches = 0;
+    c->prof_used = 0;
+    const u64 n = c->n_bytes;
+    if (c->world == 1 && n < 2 && !encode)
+    {
+        set_error("Error: File contains less than 2 characters"); // bpe.c:560
+        return BPE_CUDA_ERR_SHORT;
+    }
+    if ((rc = ensure_stream_buffers(c, n)))
+        return rc;
+    if (!c->d_dense)
+        CU(cudaMalloc(&c->d_dense, 65536 * sizeof(u32)));
+    if (!c->d_part)
+    {
+        c->sel_grid = c->sm_count * 2;
+        CU(cudaMalloc(&c->d_part, (size_t)c->sel_grid * sizeof(SelPart)));
+    }
+    // fresh table
+    if (c->d_tkey)
+    {
+        CU(cudaFree(c->d_tkey));
+        CU(cudaFree(c->d_tmeta));
+        c->d_tkey = c->d_tmeta = nullptr;
+    }
+    c->tcap = 1ull << 20;
+    if ((rc = table_alloc(c, c->tcap, &c->d_tkey, &c->d_tmeta)))
+        return rc;
+    if (c->merges_cap == 0)
+    {
+        c->merges_cap = 8192;
+        CU(cudaMalloc(&c->d_merges, c->merges_cap * 2 * sizeof(u32)));
+        CU(cudaMalloc(&c->d_nhist, (c->merges_cap + 1) * sizeof(u64)));
+    }
+    if (encode)
+    {
+        if (n_enc + 1 > c->enc_cap)
+        {
+            if (c->d_enc_merges)
+                CU(cudaFree(c->d_enc_merges));
+            c->d_enc_merges = nullptr;
+            CU(cudaMalloc(&c->d_enc_merges, (n_enc + 1) * 2 * sizeof(u32)));
+            c->enc_cap = n_enc + 1;
+        }
+        if (n_enc)
+            CU(cudaMemcpyAsync(c->d_enc_merges, enc_merges, n_enc * sizeof(bpe_pair_t), cudaMemcpyHostToDevice, c->stream));
+    }
+    if ((rc = ensure_delta(c, 8192)))
+        return rc;
+    CU(cudaMemsetAsync(c->d_delta, 0, c->delta_cap * sizeof(int32_t), c->stream));
+    if (c->world > 1)
+        CU(cudaMemsetAsync(c->d_delta_red, 0, c->delta_cap * sizeof(int32_t), c->stream));
+    CU(cudaMemsetAsync(c->d_desc, 0, c->desc_cap * sizeof(u64), c->stream));
+    CU(cudaMemsetAsync(c->d_pdesc, 0, c->desc_cap * sizeof(u32), c->stream));
+    CU(cudaMemsetAsync(c->d_dense, 0, 65536 * sizeof(u32), c->stream));
+    if (c->profile_replace && c->prof.empty())
+    {
+        c->prof.resize(2 * 70000);
+        for (auto &e : c->prof)
+            CU(cudaEventCreate(&e));
+    }
+    if ((rc = init_state(c, n, max_merges, encode, n_enc)))
+        return rc;
+
+    cudaEvent_t ev0, ev1;
+    CU(cudaEventCreate(&ev0));
+    CU(cudaEventCreate(&ev1));
+    CU(cudaEventRecord(ev0, c->stream));
+
+    // K0 + K1: widen and count byte pairs
+    if (n)
+    {
+        const u64 nvec = (n + 15) / 16;
+        const int grid = (int)std::min<u64>((nvec + 255) / 256, (u64)c->sm_count * 3);
+        widen_count_kernel<<<grid, 256, 128 * 128 * sizeof(u32), c->stream>>>(c->d_bytes, n, c->d_tok_alloc[0] + 4, c->d_dense);
+        c->launches++;
+    }
+    if (c->world > 1)
+    {
+        edge_record_kernel<<<1, 32, 0, c->stream>>>(c->d_st, c->d_delta, 0);
+        NC(g_nccl.AllReduce(c->d_delta, c->d_delta_red, HDR_INTS, ncclInt32, ncclSum, c->comm, c->stream));
+        resolve_edges_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_delta_red);
+        boundary_pair_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_dense);
+        NC(g_nccl.AllReduce(c->d_dense, c->d_dense, 65536, ncclUint32, ncclSum, c->comm, c->stream));
+        c->launches += 3;
+    }
+    table_from_dense_kernel<<<65536 / 256, 256, 0, c->stream>>>(c->d_st, c->d_dense);
+    c->launches++;
+    CU(cudaGetLastError());
+
+    // the reference slices statically below 1,048,576 tokens (bpe.c:449): known up front for small inputs
+    if ((rc = poll_state(c)))
+        return rc;
+    {
+        u64 n_global = c->h_st->n_global;
+        if (c->world > 1)
+        {
+            // header of the reduced buffer holds every rank's length
+            std::vector<u32> hdr(HDR_INTS);
+            CU(cudaMemcpyAsync(hdr.data(), c->d_delta_red, HDR_INTS * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            n_global = 0;
+            for (int r = 0; r < c->world; r++)
+                n_global += (u64)hdr[r * REC_INTS] | ((u64)hdr[r * REC_INTS + 1] << 32);
+        }
+        c->stats.n_input = n_global;
+        if (!encode && n_global < 2)
+        {
+            set_error("Error: File contains less than 2 characters");
+            return BPE_CUDA_ERR_SHORT;
+        }
+        if (!encode && n_global < STATIC_LIMIT)
+        {
+            const u32 one = 1;
+            CU(cudaMemcpyAsync(&c->d_st->static_mode, &one, sizeof one, cudaMemcpyHostToDevice, c->stream));
+            c->h_st->static_mode = 1;
+        }
+    }
+
+    if ((rc = run_loop(c, encode)))
+        return rc;
+
+    CU(cudaEventRecord(ev1, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ev0, ev1));
+    CU(cudaEventDestroy(ev0));
+    CU(cudaEventDestroy(ev1));
+
+    DevState *h = c->h_st;
+    c->res_n_merges = (size_t)h->merges_done;
+    c->res_n_tokens = (size_t)h->n;
+    c->stats.n_merges = h->merges_done;
+    c->stats.n_tokens = (c->world > 1) ? h->n_global : h->n;
+    c->stats.ranks_applied = h->ranks_applied;
+    c->stats.same_bucket_ties = h->same_bucket_ties;
+    c->stats.threshold_edges = h->threshold_edges;
+    c->stats.table_capacity = c->tcap;
+    c->stats.final_distinct = (u64)h->distinct;
+    c->stats.kernel_launches = c->launches;
+    c->stats.ms_device = ms;
+    // algorithmic bytes of the replace passes: 4*(n_k + n_{k+1}) per merge that ran a pass
+    if (h->merges_done)
+    {
+        std::vector<u64> nh(h->merges_done);
+        CU(cudaMemcpy(nh.data(), c->d_nhist, h->merges_done * sizeof(u64), cudaMemcpyDeviceToHost));
+        u64 bytes = 0;
+        for (u64 k = 0; k < h->merges_done; k++)
+        {
+            const u64 nk = nh[k], nk1 = (k + 1 < h->merges_done) ? nh[k + 1] : c->stats.n_tokens;
+            if (!encode || nk1 != nk)
+                bytes += 4 * (nk + nk1);
+        }
+        c->stats.replace_bytes = bytes;
+    }
+    if (c->profile_replace)
+    {
+        double tot = 0;
+        for (size_t i = 0; i + 1 < c->prof_used; i += 2)
+        {
+            float e = 0;
+            CU(cudaEventElapsedTime(&e, c->prof[i], c->prof[i + 1]));
+            tot += e;
+        }
+        c->stats.replace_ms = tot;
+    }
+    c->stats.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (stats_out)
+        *stats_out = c->stats;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pause handling
+__global__ void tier_a_commit_kernel(DevState *st, const int32_t *delta_reduced)
+{
+    // Provisional: takes the first maximal slot.  Replaced by the exact chain-order resolver.
+    if (st->stop != STOP_PAUSE)
+        return;
+    const u64 key = st->tkey[st->sel_slot];
+    commit_merge(st, (u32)(key & 0xFFFFFFFFull), (u32)(key >> 32), (u32)(st->sel_key >> 32),
+                 reinterpret_cast<const u32 *>(delta_reduced));
+    st->stop = STOP_RUN;
+    st->pause = 0;
+}
+
+static int resolve_pause(bpe_cuda_ctx *c, bool encode)
+{
+    DevState *h = c->h_st;
+    int rc;
+    if (h->pause & PAUSE_STATIC)
+    {
+        // the select kernel latched static_mode; nothing else to do but resume
+        resume_kernel<<<1, 1, 0, c->stream>>>(c->d_st);
+        c->launches++;
+        return 0;
+    }
+    c->stats.resolver_runs++;
+    if ((rc = ensure_delta(c, (size_t)(256 + h->merges_done + 2))))
+        return rc;
+    if ((rc = ensure_logs(c, (size_t)(h->merges_done + 2))))
+        return rc;
+    tier_a_commit_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_delta_red);
+    c->launches++;
+    return enqueue_step(c, (u32)(256 + h->merges_done), h->n, encode, false);
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+extern "C"
+{
+
+const char *bpe_cuda_last_error(void) { return g_err[0] ? g_err : g_err_global; }
+
+void bpe_cuda_free(void *p) { free(p); }
+
+int bpe_cuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+        return 0;
+    return n;
+}
+
+int bpe_cuda_ctx_create(int device, bpe_cuda_ctx_t **out)
+{
+    if (!out)
+        return BPE_CUDA_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev)
+    {
+        set_error("no CUDA device %d (%d visible); this engine has no CPU fallback", device, ndev);
+        return BPE_CUDA_ERR_CUDA;
+    }
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+    {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return BPE_CUDA_ERR_CUDA;
+    }
+    bpe_cuda_ctx *c = new bpe_cuda_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&c->d_st, sizeof(DevState)) != cudaSuccess ||
+        cudaMallocHost(&c->h_st, sizeof(DevState)) != cudaSuccess)
+    {
+        set_error("context allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return BPE_CUDA_ERR_CUDA;
+    }
+    memset(&c->stats, 0, sizeof c->stats);
+    int rc = setup_kernels(c);
+    if (rc)
+    {
+        delete c;
+        return rc;
+    }
+    if (const char *e = getenv("BPE_CUDA_BATCH_STEPS"))
+        c->batch_steps = std::max(1, atoi(e));
+    if (const char *e = getenv("BPE_CUDA_SMEM_HIST_MAX_VOCAB"))
+        c->smem_hist_max_vocab = atoi(e);
+    *out = c;
+    return 0;
+}
+
+void bpe_cuda_ctx_destroy(bpe_cuda_ctx_t *c)
+{
+    if (!c)
+        return;
+    cudaSetDevice(c->device);
+    if (c->stream)
+        cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy)
+        g_nccl.CommDestroy(c->comm);
+    for (auto &e : c->prof)
+        cudaEventDestroy(e);
+    cudaFree(c->d_bytes);
+    cudaFree(c->d_tok_alloc[0]);
+    cudaFree(c->d_tok_alloc[1]);
+    cudaFree(c->d_st);
+    cudaFreeHost(c->h_st);
+    cudaFree(c->d_desc);
+    cudaFree(c->d_pdesc);
+    cudaFree(c->d_delta);
+    if (c->d_delta_red != c->d_delta)
+        cudaFree(c->d_delta_red);
+    cudaFree(c->d_tkey);
+    cudaFree(c->d_tmeta);
+    cudaFree(c->d_merges);
+    cudaFree(c->d_nhist);
+    cudaFree(c->d_enc_merges);
+    cudaFree(c->d_part);
+    cudaFree(c->d_dense);
+    if (c->stream)
+        cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int bpe_cuda_nccl_unique_id(void *id128)
+{
+    if (!id128)
+        return BPE_CUDA_ERR_ARG;
+    int rc = nccl_load();
+    if (rc)
+        return rc;
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    memcpy(id128, &id, 128);
+    return 0;
+}
+
+int bpe_cuda_ctx_set_comm(bpe_cuda_ctx_t *c, int rank, int world, const void *id128)
+{
+    if (!c || !id128 || world < 1 || world > MAX_RANKS || rank < 0 || rank >= world)
+        return BPE_CUDA_ERR_ARG;
+    if (world == 1)
+    {
+        c->rank = 0;
+        c->world = 1;
+        return 0;
+    }
+    int rc = nccl_load();
+    if (rc)
+        return rc;
+    CU(cudaSetDevice(c->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NC(g_nccl.CommInitRank(&c->comm, world, id, rank));
+    c->rank = rank;
+    c->world = world;
+    // the reduced-delta buffer becomes a separate allocation
+    if (c->d_delta)
+    {
+        cudaFree(c->d_delta);
+        c->d_delta = c->d_delta_red = nullptr;
+        c->delta_cap = 0;
+    }
+    return 0;
+}
+
+int bpe_cuda_ctx_upload(bpe_cuda_ctx_t *c, const uint8_t *shard, size_t n)
+{
+    if (!c || (!shard && n))
+        return BPE_CUDA_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    int rc = ensure_bytes(c, n);
+    if (rc)
+        return rc;
+    if (n)
+        CU(cudaMemcpyAsync(c->d_bytes, shard, n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->d_bytes + n, 0, c->bytes_cap - n, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->n_bytes = n;
+    return 0;
+}
+
+int bpe_cuda_ctx_upload_device(bpe_cuda_ctx_t *c, const void *dev, size_t n)
+{
+    if (!c || (!dev && n))
+        return BPE_CUDA_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    int rc = ensure_bytes(c, n);
+    if (rc)
+        return rc;
+    if (n)
+        CU(cudaMemcpyAsync(c->d_bytes, dev, n, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemsetAsync(c->d_bytes + n, 0, c->bytes_cap - n, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->n_bytes = n;
+    return 0;
+}
+
+int bpe_cuda_ctx_train(bpe_cuda_ctx_t *c, uint64_t max_merges, bpe_cuda_stats_t *stats)
+{
+    if (!c)
+        return BPE_CUDA_ERR_ARG;
+    return run_common(c, max_merges, nullptr, 0, false, stats);
+}
+
+int bpe_cuda_ctx_encode(bpe_cuda_ctx_t *c, const bpe_pair_t *merges, size_t n_merges, bpe_cuda_stats_t *stats)
+{
+    if (!c || (!merges && n_merges))
+        return BPE_CUDA_ERR_ARG;
+    for (size_t r = 0; r < n_merges; r++)
+        if (merges[r].a >= 256 + r || merges[r].b >= 256 + r)
+        {
+            set_error("merge %zu refers to an id that does not exist yet", r);
+            return BPE_CUDA_ERR_ARG;
+        }
+    return run_common(c, n_merges, merges, n_merges, true, stats);
+}
+
+int bpe_cuda_ctx_result_sizes(bpe_cuda_ctx_t *c, size_t *n_merges, size_t *n_tokens_local)
+{
+    if (!c)
+        return BPE_CUDA_ERR_ARG;
+    if (n_merges)
+        *n_merges = c->res_n_merges;
+    if (n_tokens_local)
+        *n_tokens_local = c->res_n_tokens;
+    return 0;
+}
+
+const uint32_t *bpe_cuda_ctx_device_tokens(bpe_cuda_ctx_t *c)
+{
+    if (!c || !c->h_st)
+        return nullptr;
+    return c->h_st->tok[c->h_st->cur];
+}
+
+int bpe_cuda_ctx_download(bpe_cuda_ctx_t *c, bpe_pair_t *merges, uint32_t *tokens)
+{
+    if (!c)
+        return BPE_CUDA_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    if (merges && c->res_n_merges)
+        CU(cudaMemcpyAsync(merges, c->d_merges, c->res_n_merges * sizeof(bpe_pair_t), cudaMemcpyDeviceToHost, c->stream));
+    if (tokens && c->res_n_tokens)
+        CU(cudaMemcpyAsync(tokens, c->h_st->tok[c->h_st->cur], c->res_n_tokens * sizeof(u32), cudaMemcpyDeviceToHost,
+                           c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int bpe_cuda_ctx_set_option(bpe_cuda_ctx_t *c, const char *name, long long value)
+{
+    if (!c || !name)
+        return BPE_CUDA_ERR_ARG;
+    if (!strcmp(name, "profile_replace"))
+        c->profile_replace = (int)value;
+    else if (!strcmp(name, "batch_steps"))
+        c->batch_steps = (int)std::max<long long>(1, value);
+    else if (!strcmp(name, "smem_hist_max_vocab"))
+        c->smem_hist_max_vocab = (int)value;
+    else if (!strcmp(name, "force_census"))
+        c->force_census = (int)value;
+    else
+        return BPE_CUDA_ERR_ARG;
+    return 0;
+}
+
+// ---- one-call entry points -------------------------------------------------------------------
+struct RankJob
+{
+    int rank, world, rc;
+    const uint8_t *bytes;
+    size_t n;
+    ncclUniqueId id;
+    uint64_t max_merges;
+    const bpe_pair_t *enc;
+    size_t n_enc;
+    bool encode;
+    std::vector<bpe_pair_t> merges;
+    std::vector<u32> tokens;
+    bpe_cuda_stats_t stats;
+    char err[512];
+};
+
+static void rank_main(RankJob *j)
+{
+    bpe_cuda_ctx_t *c = nullptr;
+    j->err[0] = 0;
+    auto fail = [&](int rc) {
+        j->rc = rc;
+        snprintf(j->err, sizeof j->err, "%s", bpe_cuda_last_error());
+        if (c)
+            bpe_cuda_ctx_destroy(c);
+    };
+    int rc = bpe_cuda_ctx_create(j->rank, &c);
+    if (rc)
+        return fail(rc);
+    if (j->world > 1 && (rc = bpe_cuda_ctx_set_comm(c, j->rank, j->world, &j->id)))
+        return fail(rc);
+    const auto t0 = std::chrono::steady_clock::now();
+    if ((rc = bpe_cuda_ctx_upload(c, j->bytes, j->n)))
+        return fail(rc);
+    const double ms_h2d = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    rc = j->encode ? bpe_cuda_ctx_encode(c, j->enc, j->n_enc, &j->stats) : bpe_cuda_ctx_train(c, j->max_merges, &j->stats);
+    if (rc)
+        return fail(rc);
+    size_t nm = 0, nt = 0;
+    bpe_cuda_ctx_result_sizes(c, &nm, &nt);
+    j->merges.resize(nm);
+    j->tokens.resize(nt);
+    const auto t1 = std::chrono::steady_clock::now();
+    if ((rc = bpe_cuda_ctx_download(c, j->merges.data(), j->tokens.data())))
+        return fail(rc);
+    j->stats.ms_h2d = ms_h2d;
+    j->stats.ms_d2h = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+    j->rc = 0;
+    bpe_cuda_ctx_destroy(c);
+}
+
+static int run_host(const uint8_t *bytes, size_t n_in, uint64_t max_merges, const bpe_pair_t *enc, size_t n_enc, bool encode,
+                    int n_gpus, bpe_pair_t **merges_out, size_t *n_merges, uint32_t **tokens_out, size_t *n_tokens,
+                    bpe_cuda_stats_t *stats)
+{
+    if (!bytes || !tokens_out || !n_tokens || (!encode && (!merges_out || !n_merges)) || n_gpus < 1 || n_gpus > MAX_RANKS)
+    {
+        set_error("invalid argument");
+        return BPE_CUDA_ERR_ARG;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    size_t n = 0;
+    {
+        const void *z = memchr(bytes, 0, n_in); // strlen semantics, bpe.c:555
+        n = z ? (size_t)((const uint8_t *)z - bytes) : n_in;
+    }
+    if (!encode && n < 2)
+    {
+        set_error("Error: File contains less than 2 characters");
+        return BPE_CUDA_ERR_SHORT;
+    }
+    std::vector<RankJob> jobs((size_t)n_gpus);
+    ncclUniqueId id;
+    memset(&id, 0, sizeof id);
+    if (n_gpus > 1)
+    {
+        int rc = bpe_cuda_nccl_unique_id(&id);
+        if (rc)
+            return rc;
+    }
+    for (int r = 0; r < n_gpus; r++)
+    {
+        RankJob &j = jobs[(size_t)r];
+        const size_t lo = (size_t)((unsigned __int128)n * (unsigned)r / (unsigned)n_gpus);
+        const size_t hi = (size_t)((unsigned __int128)n * (unsigned)(r + 1) / (unsigned)n_gpus);
+        j.rank = r;
+        j.world = n_gpus;
+        j.rc = -1;
+        j.bytes = bytes + lo;
+        j.n = hi - lo;
+        j.id = id;
+        j.max_merges = max_merges;
+        j.enc = enc;
+        j.n_enc = n_enc;
+        j.encode = encode;
+    }
+    if (n_gpus == 1)
+        rank_main(&jobs[0]);
+    else
+    {
+        std::vector<std::thread> th;
+        for (int r = 0; r < n_gpus; r++)
+            th.emplace_back(rank_main, &jobs[(size_t)r]);
+        for (auto &t : th)
+            t.join();
+    }
+    for (auto &j : jobs)
+        if (j.rc)
+        {
+            set_error("rank %d: %s", j.rank, j.err);
+            return j.rc;
+        }
+    size_t total = 0;
+    for (auto &j : jobs)
+        total += j.tokens.size();
+    u32 *toks = (u32 *)malloc((total ? total : 1) * sizeof(u32));
+    if (!toks)
+        return BPE_CUDA_ERR_NOMEM;
+    size_t off = 0;
+    for (auto &j : jobs)
+    {
+        if (!j.tokens.empty())
+            memcpy(toks + off, j.tokens.data(), j.tokens.size() * sizeof(u32));
+        off += j.tokens.size();
+    }
+    if (merges_out)
+    {
+        const size_t nm = jobs[0].merges.size();
+        bpe_pair_t *mg = (bpe_pair_t *)malloc((nm ? nm : 1) * sizeof(bpe_pair_t));
+        if (!mg)
+        {
+            free(toks);
+            return BPE_CUDA_ERR_NOMEM;
+        }
+        if (nm)
+            memcpy(mg, jobs[0].merges.data(), nm * sizeof(bpe_pair_t));
+        *merges_out = mg;
+        *n_merges = nm;
+    }
+    *tokens_out = toks;
+    *n_tokens = total;
+    if (stats)
+    {
+        *stats = jobs[0].stats;
+        for (auto &j : jobs)
+        {
+            stats->ms_device = std::max(stats->ms_device, j.stats.ms_device);
+            stats->ms_h2d = std::max(stats->ms_h2d, j.stats.ms_h2d);
+            stats->ms_d2h = std::max(stats->ms_d2h, j.stats.ms_d2h);
+        }
+        stats->n_tokens = total;
+        stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return 0;
+}
+
+int bpe_cuda_train(const uint8_t *bytes, size_t n, uint64_t max_merges, int n_gpus, bpe_pair_t **merges_out, size_t *n_merges,
+                   uint32_t **tokens_out, size_t *n_tokens, bpe_cuda_stats_t *stats)
+{
+    return run_host(bytes, n, max_merges, nullptr, 0, false, n_gpus, merges_out, n_merges, tokens_out, n_tokens, stats);
+}
+
+int bpe_cuda_encode(const uint8_t *bytes, size_t n, const bpe_pair_t *merges, size_t n_merges, int n_gpus,
+                    uint32_t **tokens_out, size_t *n_tokens, bpe_cuda_stats_t *stats)
+{
+    if (!merges && n_merges)
+        return BPE_CUDA_ERR_ARG;
+    return run_host(bytes, n, 0, merges, n_merges, true, n_gpus, nullptr, nullptr, tokens_out, n_tokens, stats);
+}
+
+} // extern "C"

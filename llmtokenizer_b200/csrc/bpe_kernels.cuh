@@ -1,0 +1,1145 @@
+// Device side of the B200 BPE merge-loop engine (sm_100a).
+//
+// Reference path being replaced (file:line relative to the reference tree):
+//   widen            bpe/src/bpe.c:580-584
+//   pair count       bpe/src/bpe.c:428-527 (get_freq) + hash_table/src/hash_table.c:109-193 (merge)
+//   argmax           bpe/src/bpe.c:705-750 + dyn_arr/src/dyn_arr.c:136-181 (first maximum wins)
+//   rewrite          bpe/src/bpe.c:760-779
+//
+// Everything here is integer work bounded by HBM bandwidth; nothing is a dense contraction, so
+// tensor cores / TMEM are deliberately unused.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bpe
+{
+
+typedef unsigned long long u64;
+typedef long long i64;
+typedef uint32_t u32;
+
+constexpr u32 SENT = 0xFFFFFFFFu; // "no token": stream start / end inside halo windows
+constexpr u64 EMPTY_KEY = ~0ull;
+constexpr u64 NO_SLOT = ~0ull;
+
+constexpr int MAX_RANKS = 8;
+constexpr int REC_INTS = 8;                    // one edge record
+constexpr int HDR_INTS = MAX_RANKS * REC_INTS; // edge records sit in front of the delta vectors
+
+constexpr u64 STATIC_LIMIT = 65536ull * 16ull; // bpe.c:423,449: below this the reference slices statically
+constexpr int REF_THREADS = 16;                // bpe.c:409
+
+enum : u32
+{
+    STOP_RUN = 0,
+    STOP_DONE = 1,
+    STOP_PAUSE = 2,
+    STOP_ERROR = 3
+};
+enum : u32
+{
+    PAUSE_TIE = 1,   // >= 2 maximal pairs share the winning bucket: chain order decides
+    PAUSE_EDGE = 2,  // D sits exactly on a doubling threshold of the merged table
+    PAUSE_STATIC = 4 // stream fell below 1,048,576 tokens: reference switches to static slicing
+};
+enum : u32
+{
+    ERR_TABLE_FULL = 1,
+    ERR_MISSING_KEY = 2,
+    ERR_NEGATIVE = 4,
+    ERR_PROBE = 8
+};
+
+// Device-resident control block.  Everything a merge step needs lives here, so a step is a fixed
+// sequence of launches with no host round trip.
+struct DevState
+{
+    // token stream, ping-pong (pointers are 16 B aligned; 4 readable slots in front of each)
+    u32 *tok[2];
+    u32 cur;
+    u32 epoch;  // bumped per merge; stamps tile descriptors so they never need clearing
+    u64 n;      // tokens in tok[cur] (this rank's shard)
+    u64 n_next; // written by the replace kernel
+    u64 n_global;
+    // selected merge
+    u32 a, b, z, freq;
+    u32 skip; // encode: this rank's pair does not occur anywhere -> no pass
+    // loop control
+    u32 stop, pause, err, static_mode;
+    u64 merges_done, max_merges;
+    // pair table: open addressing, key = a | b<<32, meta = murmur3 | count<<32
+    u64 *tkey;
+    u64 *tmeta;
+    u64 tcap;
+    i64 distinct; // D: keys with count > 0
+    u64 occupied; // claimed slots (dead keys included)
+    // scheduling counters
+    u32 ticket, sel_done;
+    // selection result (kept for the resolver)
+    u64 sel_key, sel_slot;
+    u32 sel_mult, sel_pad;
+    // statistics
+    u64 same_bucket_ties, threshold_edges;
+    // shard edges (single GPU: SENT / 0)
+    u32 halo_before[2], halo_after[3], carry_in;
+    u32 rank, world;
+    // the reference's 16 worker tables keep their grown bucket count across iterations
+    u64 bt[REF_THREADS];
+    // logs
+    u32 *merges; // pairs, 2 u32 each
+    u64 *n_hist; // global token count before merge k
+    // encode
+    const u32 *enc_merges;
+    u64 enc_total;
+    u64 ranks_applied;
+};
+
+// ---------------------------------------------------------------------------------------------
+// hash_table.c:8-53 on the 8-byte key {u32 a; u32 b}
+__host__ __device__ __forceinline__ u32 rotl32(u32 x, int r) { return (x << r) | (x >> (32 - r)); }
+
+__host__ __device__ __forceinline__ u32 murmur3_pair(u32 a, u32 b)
+{
+    u32 h = 0x9747b28cu;
+    u32 k = a;
+    k *= 0xcc9e2d51u;
+    k = rotl32(k, 15);
+    k *= 0x1b873593u;
+    h ^= k;
+    h = rotl32(h, 13);
+    h = h * 5u + 0xe6546b64u;
+    k = b;
+    k *= 0xcc9e2d51u;
+    k = rotl32(k, 15);
+    k *= 0x1b873593u;
+    h ^= k;
+    h = rotl32(h, 13);
+    h = h * 5u + 0xe6546b64u;
+    h ^= 8u;
+    h ^= h >> 16;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    return h;
+}
+
+// hash_table.c:6,248: a table doubles at the top of an insert call once nodes >= 0.3 * buckets
+__host__ __device__ __forceinline__ bool resize_due(u64 nodes, u64 buckets)
+{
+    return (double)nodes >= 0.3 * (double)buckets;
+}
+__host__ __device__ inline u64 resize_threshold(u64 buckets)
+{
+    u64 t = (u64)(0.3 * (double)buckets);
+    while (!resize_due(t, buckets))
+        t++;
+    while (t > 0 && resize_due(t - 1, buckets))
+        t--;
+    return t;
+}
+// bucket count of the merged table (fresh 65,536 buckets every iteration, bpe.c:611,684) once D
+// keys went in, away from the exact-threshold edge (handled by the resolver)
+__host__ __device__ inline u64 merged_buckets(u64 distinct)
+{
+    u64 b = 65536;
+    while (distinct > resize_threshold(b))
+        b *= 2;
+    return b;
+}
+__host__ __device__ inline bool on_threshold(u64 distinct)
+{
+    for (u64 b = 65536;; b *= 2)
+    {
+        const u64 t = resize_threshold(b);
+        if (t == distinct)
+            return true;
+        if (t > distinct)
+            return false;
+    }
+}
+// growth of a table that starts an iteration with b0 buckets, sees d distinct keys, and whose
+// very last insert call did / did not create the d-th key
+__host__ __device__ inline u64 grown_buckets(u64 b0, u64 d, bool last_call_is_new)
+{
+    u64 b = b0;
+    for (;;)
+    {
+        const u64 th = resize_threshold(b);
+        if (d > th || (d == th && !last_call_is_new))
+            b *= 2;
+        else
+            return b;
+    }
+}
+__host__ __device__ inline u32 doublings_after(u64 b0, u64 bfinal, u64 r)
+{
+    u32 c = 0;
+    for (u64 b = b0; b < bfinal; b *= 2)
+        if (resize_threshold(b) >= r)
+            c++;
+    return c;
+}
+// position inside one chain as a sortable number (each doubling reverses every chain)
+__host__ __device__ __forceinline__ u64 chain_slot(u32 doublings_to_come, u64 r)
+{
+    return (doublings_to_come & 1u) ? ((1ull << 40) | r) : ((1ull << 40) - 1 - r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pair table
+__device__ __forceinline__ u64 probe_start(u32 h, u64 cap) { return (((u64)h * 0x9E3779B97F4A7C15ull) >> 20) & (cap - 1); }
+__device__ __forceinline__ u32 *cnt_ptr(u64 *meta, u64 slot) { return reinterpret_cast<u32 *>(meta + slot) + 1; }
+__device__ __forceinline__ u32 *hsh_ptr(u64 *meta, u64 slot) { return reinterpret_cast<u32 *>(meta + slot); }
+
+__device__ __forceinline__ u64 table_find(const u64 *tkey, u64 cap, u64 key, u32 h)
+{
+    u64 s = probe_start(h, cap);
+    for (u64 i = 0; i < cap; i++)
+    {
+        const u64 k = tkey[s];
+        if (k == key)
+            return s;
+        if (k == EMPTY_KEY)
+            return NO_SLOT;
+        s = (s + 1) & (cap - 1);
+    }
+    return NO_SLOT;
+}
+
+__device__ __forceinline__ u64 table_insert(DevState *st, u64 key, u32 h)
+{
+    u64 *tkey = st->tkey;
+    const u64 cap = st->tcap;
+    u64 s = probe_start(h, cap);
+    for (u64 i = 0; i < cap; i++)
+    {
+        u64 k = tkey[s];
+        if (k == EMPTY_KEY)
+        {
+            k = atomicCAS(tkey + s, EMPTY_KEY, key);
+            if (k == EMPTY_KEY)
+            {
+                *hsh_ptr(st->tmeta, s) = h;
+                atomicAdd(&st->occupied, 1ull);
+                return s;
+            }
+        }
+        if (k == key)
+            return s;
+        s = (s + 1) & (cap - 1);
+    }
+    return NO_SLOT;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0 + K1: widen bytes to u32 tokens (bpe.c:580-584) and histogram all adjacent byte pairs into
+// a dense 256x256 table (every overlapping occurrence counts, bpe.c:460-471).  While all ids are
+// < 256 the dense table replaces the hash table.  16 bytes per thread: one 128-bit load, four
+// 128-bit stores.
+__global__ void __launch_bounds__(256) widen_count_kernel(const uint8_t *__restrict__ bytes, u64 n, u32 *__restrict__ tok,
+                                                          u32 *__restrict__ dense)
+{
+    extern __shared__ __align__(16) u32 s_lo[]; // 128*128 privatised counts for pairs of 7-bit bytes (ASCII text)
+    for (int i = threadIdx.x; i < 128 * 128; i += blockDim.x)
+        s_lo[i] = 0;
+    __syncthreads();
+    const u64 nvec = (n + 15) / 16;
+    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (u64)gridDim.x * blockDim.x)
+    {
+        const u64 base = v * 16;
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(bytes) + v);
+        u32 c[17];
+        const u32 qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            c[k] = (qq[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
+        c[16] = (base + 16 < n) ? (u32)bytes[base + 16] : 0u;
+        uint4 *o = reinterpret_cast<uint4 *>(tok + base);
+        o[0] = make_uint4(c[0], c[1], c[2], c[3]);
+        o[1] = make_uint4(c[4], c[5], c[6], c[7]);
+        o[2] = make_uint4(c[8], c[9], c[10], c[11]);
+        o[3] = make_uint4(c[12], c[13], c[14], c[15]);
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+        {
+            if (base + k + 1 < n)
+            {
+                const u32 x = c[k], y = c[k + 1];
+                if ((x | y) < 128u)
+                    atomicAdd(&s_lo[x * 128 + y], 1u);
+                else
+                    atomicAdd(&dense[x * 256 + y], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 128 * 128; i += blockDim.x)
+    {
+        const u32 v = s_lo[i];
+        if (v)
+            atomicAdd(&dense[(i >> 7) * 256 + (i & 127)], v);
+    }
+}
+
+// the pair that straddles two shards is counted by the left shard (its first token is the left
+// shard's last): one thread, after the edge records are known
+__global__ void boundary_pair_kernel(DevState *st, u32 *dense)
+{
+    if (st->n == 0 || st->halo_after[0] == SENT)
+        return;
+    const u32 x = st->tok[st->cur][st->n - 1], y = st->halo_after[0];
+    atomicAdd(&dense[x * 256 + y], 1u);
+}
+
+__global__ void table_from_dense_kernel(DevState *st, const u32 *__restrict__ dense)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 65536)
+        return;
+    const u32 c = dense[i];
+    if (!c)
+        return;
+    const u32 a = i >> 8, b = i & 255u;
+    const u64 s = table_insert(st, (u64)a | ((u64)b << 32), murmur3_pair(a, b));
+    if (s == NO_SLOT)
+    {
+        atomicOr(&st->err, ERR_TABLE_FULL);
+        return;
+    }
+    atomicAdd(cnt_ptr(st->tmeta, s), c);
+    atomicAdd(reinterpret_cast<u64 *>(&st->distinct), 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------
+// table maintenance: copy the live entries into a fresh (larger or purged) table
+__global__ void rehash_kernel(const u64 *__restrict__ okey, const u64 *__restrict__ ometa, u64 ocap, u64 *nkey, u64 *nmeta,
+                              u64 ncap, u32 *err)
+{
+    for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < ocap; s += (u64)gridDim.x * blockDim.x)
+    {
+        const u64 k = okey[s];
+        const u64 m = ometa[s];
+        if (k == EMPTY_KEY || (m >> 32) == 0)
+            continue;
+        u64 p = probe_start((u32)m, ncap);
+        bool placed = false;
+        for (u64 i = 0; i < ncap; i++)
+        {
+            if (atomicCAS(nkey + p, EMPTY_KEY, k) == EMPTY_KEY)
+            {
+                nmeta[p] = m;
+                placed = true;
+                break;
+            }
+            p = (p + 1) & (ncap - 1);
+        }
+        if (!placed)
+            atomicOr(err, ERR_TABLE_FULL);
+    }
+}
+
+__global__ void table_swap_kernel(DevState *st, u64 *nkey, u64 *nmeta, u64 ncap)
+{
+    st->tkey = nkey;
+    st->tmeta = nmeta;
+    st->tcap = ncap;
+    st->occupied = (u64)st->distinct;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU shard edges.  After every pass each rank publishes a pair-independent record of its
+// shard (length, first three tokens, last two tokens, parity of its trailing run of equal tokens
+// and whether the whole shard is that one run) in its slot of the buffer that the per-merge
+// all-reduce sums; disjoint slots make the sum an all-gather, so there is ONE collective per merge.
+//   rec[0..1] = length (lo, hi)   rec[2..4] = first tokens   rec[5..6] = last two tokens
+//   rec[7]    = trailing-run parity | uniform<<1
+__global__ void edge_record_kernel(DevState *st, int32_t *delta_local, int use_next)
+{
+    if (st->stop != STOP_RUN && use_next)
+        return;
+    const u32 *s = use_next ? st->tok[st->cur ^ 1] : st->tok[st->cur];
+    const u64 len = (use_next && !st->skip) ? st->n_next : st->n;
+    if (use_next && st->skip)
+        s = st->tok[st->cur];
+    const int lane = threadIdx.x;
+    u32 *rec = reinterpret_cast<u32 *>(delta_local) + st->rank * REC_INTS;
+    // trailing run of the last token, 32 tokens per step
+    u64 run = 0;
+    bool uniform = false;
+    if (len)
+    {
+        const u32 last = s[len - 1];
+        u64 pos = len; // tokens [pos, len) are known to equal `last`
+        for (;;)
+        {
+            const i64 i = (i64)pos - 1 - lane;
+            const bool eq = (i >= 0) && (s[i] == last);
+            const u32 m = __ballot_sync(0xFFFFFFFFu, eq);
+            const int c = (m == 0xFFFFFFFFu) ? 32 : (__ffs(~m) - 1);
+            run += (u64)c;
+            pos -= (u64)c;
+            if (c < 32 || pos == 0)
+                break;
+        }
+        uniform = (run == len);
+    }
+    if (lane == 0)
+    {
+        rec[0] = (u32)len;
+        rec[1] = (u32)(len >> 32);
+        for (int k = 0; k < 3; k++)
+            rec[2 + k] = ((u64)k < len) ? s[k] : SENT;
+        rec[6] = len >= 1 ? s[len - 1] : SENT;
+        rec[5] = len >= 2 ? s[len - 2] : SENT;
+        rec[7] = (u32)(run & 1ull) | ((u32)uniform << 1);
+    }
+}
+
+// derive this rank's halos from all records (device function, used once a pair is chosen)
+__device__ inline void resolve_edges(DevState *st, const u32 *rec_all, u32 a, bool same)
+{
+    const int P = (int)st->world, me = (int)st->rank;
+    u64 total = 0;
+    for (int r = 0; r < P; r++)
+        total += (u64)rec_all[r * REC_INTS] | ((u64)rec_all[r * REC_INTS + 1] << 32);
+    st->n_global = total;
+    u32 before[2] = {SENT, SENT};
+    int got = 0;
+    for (int q = me - 1; q >= 0 && got < 2; q--)
+    {
+        const u32 *rc = rec_all + q * REC_INTS;
+        const u64 len = (u64)rc[0] | ((u64)rc[1] << 32);
+        if (len >= 1 && got < 2)
+            before[1 - got++] = rc[6];
+        if (len >= 2 && got < 2)
+            before[1 - got++] = rc[5];
+    }
+    u32 after[3] = {SENT, SENT, SENT};
+    got = 0;
+    for (int q = me + 1; q < P && got < 3; q++)
+    {
+        const u32 *rc = rec_all + q * REC_INTS;
+        const u64 len = (u64)rc[0] | ((u64)rc[1] << 32);
+        for (int k = 0; k < 3 && got < 3; k++)
+            if ((u64)k < len)
+                after[got++] = rc[2 + k];
+    }
+    u32 carry = 0;
+    if (same)
+        for (int q = me - 1; q >= 0; q--)
+        {
+            const u32 *rc = rec_all + q * REC_INTS;
+            const u64 len = (u64)rc[0] | ((u64)rc[1] << 32);
+            if (!len)
+                continue;
+            if (rc[6] != a)
+                break;
+            carry ^= (rc[7] & 1u);
+            if (!(rc[7] & 2u))
+                break;
+        }
+    st->halo_before[0] = before[0];
+    st->halo_before[1] = before[1];
+    st->halo_after[0] = after[0];
+    st->halo_after[1] = after[1];
+    st->halo_after[2] = after[2];
+    st->carry_in = carry;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: most frequent pair with the reference's order (bpe.c:705-750).  The merged table is walked
+// bucket 0.., so among equal frequencies the smallest `murmur3 % B(D)` wins: one packed 64-bit key
+// (count << 32 | ~bucket) turns that into a plain max.  Warp shuffles, then a block tree, then the
+// last block folds the per-block partials.  The multiplicity of the maximal key is carried along:
+// > 1 means chain order inside one bucket decides (resolver).
+struct SelPart
+{
+    u64 key;
+    u64 slot;
+    u32 mult;
+    u32 pad;
+};
+
+__device__ __forceinline__ void sel_combine(u64 &k, u64 &s, u32 &m, u64 k2, u64 s2, u32 m2)
+{
+    if (k2 > k)
+    {
+        k = k2;
+        s = s2;
+        m = m2;
+    }
+    else if (k2 == k)
+    {
+        m += m2;
+        s = (s2 < s) ? s2 : s;
+    }
+}
+
+__device__ __forceinline__ void sel_block_reduce(u64 &k, u64 &s, u32 &m, SelPart *sm)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1)
+    {
+        const u64 k2 = __shfl_xor_sync(0xFFFFFFFFu, k, o);
+        const u64 s2 = __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        const u32 m2 = __shfl_xor_sync(0xFFFFFFFFu, m, o);
+        // xor butterflies visit each lane once, so multiplicities add exactly once
+        if (k2 > k)
+        {
+            k = k2;
+            s = s2;
+            m = m2;
+        }
+        else if (k2 == k)
+        {
+            m += m2;
+            s = (s2 < s) ? s2 : s;
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0)
+    {
+        sm[warp].key = k;
+        sm[warp].slot = s;
+        sm[warp].mult = m;
+    }
+    __syncthreads();
+    if (warp == 0)
+    {
+        k = (lane < nw) ? sm[lane].key : 0ull;
+        s = (lane < nw) ? sm[lane].slot : NO_SLOT;
+        m = (lane < nw) ? sm[lane].mult : 0u;
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+        {
+            const u64 k2 = __shfl_xor_sync(0xFFFFFFFFu, k, o);
+            const u64 s2 = __shfl_xor_sync(0xFFFFFFFFu, s, o);
+            const u32 m2 = __shfl_xor_sync(0xFFFFFFFFu, m, o);
+            if (k2 > k)
+            {
+                k = k2;
+                s = s2;
+                m = m2;
+            }
+            else if (k2 == k)
+            {
+                m += m2;
+                s = (s2 < s) ? s2 : s;
+            }
+        }
+    }
+}
+
+// record the chosen pair and prepare the pass (single thread)
+__device__ inline void commit_merge(DevState *st, u32 a, u32 b, u32 freq, const u32 *rec_all)
+{
+    const u64 k = st->merges_done;
+    st->a = a;
+    st->b = b;
+    st->z = (u32)(256 + k);
+    st->freq = freq;
+    st->skip = 0;
+    st->merges[2 * k] = a;
+    st->merges[2 * k + 1] = b;
+    if (st->world > 1)
+        resolve_edges(st, rec_all, a, a == b);
+    else
+        st->n_global = st->n;
+    st->n_hist[k] = st->n_global;
+    st->merges_done = k + 1;
+    st->epoch = st->epoch + 1;
+    st->ticket = 0;
+}
+
+constexpr int SEL_THREADS = 512;
+
+__global__ void __launch_bounds__(SEL_THREADS) select_kernel(DevState *st, SelPart *part, const int32_t *delta_reduced)
+{
+    if (st->stop != STOP_RUN)
+        return;
+    __shared__ SelPart sm[SEL_THREADS / 32];
+    __shared__ bool s_last;
+    const u64 cap = st->tcap;
+    const u64 *__restrict__ meta = st->tmeta;
+    const u64 D = (u64)st->distinct;
+    const u64 B = merged_buckets(D);
+    const u32 bmask = (u32)(B - 1);
+    u64 k = 0, s = NO_SLOT;
+    u32 m = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x)
+    {
+        const u64 mv = meta[i];
+        if (mv >> 32)
+        {
+            const u64 kk = (mv & 0xFFFFFFFF00000000ull) | (u64)(0xFFFFFFFFu - ((u32)mv & bmask));
+            sel_combine(k, s, m, kk, i, 1u);
+        }
+    }
+    sel_block_reduce(k, s, m, sm);
+    if (threadIdx.x == 0)
+    {
+        part[blockIdx.x].key = k;
+        part[blockIdx.x].slot = s;
+        part[blockIdx.x].mult = m;
+        __threadfence();
+        const u32 done = atomicAdd(&st->sel_done, 1u);
+        s_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last)
+        return;
+    __threadfence();
+    k = 0;
+    s = NO_SLOT;
+    m = 0;
+    for (u32 i = threadIdx.x; i < gridDim.x; i += blockDim.x)
+    {
+        const volatile SelPart *p = part + i;
+        sel_combine(k, s, m, p->key, p->slot, p->mult);
+    }
+    sel_block_reduce(k, s, m, sm);
+    if (threadIdx.x != 0)
+        return;
+    st->sel_done = 0;
+    st->sel_key = k;
+    st->sel_slot = s;
+    st->sel_mult = m;
+    const u32 *rec_all = reinterpret_cast<const u32 *>(delta_reduced);
+    if (st->world > 1)
+    {
+        u64 total = 0;
+        for (u32 r = 0; r < st->world; r++)
+            total += (u64)rec_all[r * REC_INTS] | ((u64)rec_all[r * REC_INTS + 1] << 32);
+        st->n_global = total;
+    }
+    else
+        st->n_global = st->n;
+    const u32 freq = (u32)(k >> 32);
+    if (D == 0 || m == 0 || freq <= 1 || st->merges_done >= st->max_merges) // bpe.c:730, bpe.c:745, cap
+    {
+        st->stop = STOP_DONE;
+        return;
+    }
+    if (!st->static_mode && st->n_global < STATIC_LIMIT)
+    {
+        st->static_mode = 1;
+        st->pause = PAUSE_STATIC;
+        st->stop = STOP_PAUSE;
+        return;
+    }
+    const bool tie = (m > 1), edge = on_threshold(D);
+    if (tie || edge)
+    {
+        if (tie)
+            st->same_bucket_ties++;
+        if (edge)
+            st->threshold_edges++;
+        st->pause = (tie ? PAUSE_TIE : 0u) | (edge ? PAUSE_EDGE : 0u);
+        st->stop = STOP_PAUSE;
+        return;
+    }
+    const u64 key = st->tkey[s];
+    commit_merge(st, (u32)(key & 0xFFFFFFFFull), (u32)(key >> 32), freq, rec_all);
+}
+
+// encode: the "selection" is simply the next rank of the given merge list; a rank whose pair does
+// not occur (count 0 in the replicated table) costs no pass
+__global__ void select_rank_kernel(DevState *st, const int32_t *delta_reduced)
+{
+    if (st->stop != STOP_RUN)
+        return;
+    const u64 r = st->merges_done;
+    if (r >= st->enc_total)
+    {
+        st->stop = STOP_DONE;
+        return;
+    }
+    const u32 a = st->enc_merges[2 * r], b = st->enc_merges[2 * r + 1];
+    const u64 slot = table_find(st->tkey, st->tcap, (u64)a | ((u64)b << 32), murmur3_pair(a, b));
+    const u32 cnt = (slot == NO_SLOT) ? 0u : *cnt_ptr(st->tmeta, slot);
+    const u32 *rec_all = reinterpret_cast<const u32 *>(delta_reduced);
+    commit_merge(st, a, b, cnt, rec_all);
+    if (cnt == 0)
+        st->skip = 1;
+    else
+        st->ranks_applied++;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: fused replace + prefix-scan compaction + pair-count deltas — the hot kernel.
+//
+// One streaming pass: 4*n_k bytes in, 4*n_{k+1} bytes out.  Persistent CTAs take tiles in ticket
+// order; a tile is staged in shared memory with 128-bit coalesced loads (two tokens of halo in
+// front, three behind), every thread then owns 15 consecutive tokens (odd stride: conflict-free
+// shared-memory access), finds the replacements that start in its window, and the kept tokens
+// are compacted through shared memory and written out coalesced.  Tile offsets come from a
+// single-pass decoupled look-back over 64-bit descriptors stamped with the merge epoch (no
+// clearing between merges).
+//
+// Replacements are greedy left to right (bpe.c:760-772).  For a != b they cannot overlap, so a
+// position starts one iff it holds a and its right neighbour holds b.  For a == b they pair up
+// from the start of each run of a, so a position starts one iff the number of a right in front of
+// it is even; that parity is carried across tiles through a second descriptor array (and across
+// shards through the edge records).
+//
+// Every replacement also reports which pair INSTANCES vanish and appear around it, into four
+// dense vectors indexed by the free token: (x,a)-, (b,y)-, (x',z)+, (z,y)+.  A replacement always
+// owns its left neighbour pair and owns its right one unless another replacement starts right
+// behind it, so each instance is charged once (abab -> zz: one (b,a) gone, one (z,z) new).  The
+// vectors live in shared memory while the vocabulary is small (hot early merges), else in global
+// memory; the table is updated from them afterwards, so the stream is never recounted.
+constexpr int R_THREADS = 256;
+constexpr int R_ITEMS = 15;
+constexpr int R_TILE = R_THREADS * R_ITEMS; // 3840 tokens, a multiple of 4
+
+constexpr u64 DESC_AGG = 1ull << 62;
+constexpr u64 DESC_INCL = 2ull << 62;
+constexpr u64 DESC_COUNT_MASK = (1ull << 40) - 1;
+__device__ __forceinline__ u64 desc_pack(u64 status, u32 epoch, u64 count)
+{
+    return status | ((u64)(epoch & 0x3FFFFFu) << 40) | (count & DESC_COUNT_MASK);
+}
+__device__ __forceinline__ bool desc_ready(u64 d, u32 epoch)
+{
+    return (d >> 62) != 0 && ((u32)(d >> 40) & 0x3FFFFFu) == (epoch & 0x3FFFFFu);
+}
+// run-parity descriptor: status(2) | all_a(1) | parity(1) | epoch(22)
+constexpr u32 PD_LOCAL = 1u << 30;
+constexpr u32 PD_RESOLVED = 2u << 30;
+__device__ __forceinline__ u32 pd_pack(u32 status, u32 epoch, u32 all_a, u32 par)
+{
+    return status | (all_a << 29) | (par << 28) | (epoch & 0x3FFFFFu);
+}
+
+template <bool SMEM_HIST>
+__global__ void __launch_bounds__(R_THREADS) replace_kernel(DevState *st, u64 *desc, u32 *pdesc, int32_t *delta)
+{
+    if (st->stop != STOP_RUN || st->skip)
+        return;
+    extern __shared__ __align__(16) u32 smem[];
+    u32 *s_tok = smem;                                             // R_TILE + 8 tokens
+    int32_t *s_hist = reinterpret_cast<int32_t *>(smem + R_TILE + 8); // 4*(z+1) counters when SMEM_HIST
+    __shared__ u32 s_warp[R_THREADS / 32];
+    __shared__ u64 s_excl;
+    __shared__ u32 s_tile, s_carry;
+
+    const u32 a = st->a, b = st->b, z = st->z;
+    const bool same = (a == b);
+    const u64 n = st->n;
+    const u32 *__restrict__ in = st->tok[st->cur];
+    u32 *__restrict__ out = st->tok[st->cur ^ 1];
+    const u32 epoch = st->epoch;
+    const u64 ntiles = (n + R_TILE - 1) / R_TILE;
+    const u32 hb0 = st->halo_before[0], hb1 = st->halo_before[1];
+    const u32 ha0 = st->halo_after[0], ha1 = st->halo_after[1], ha2 = st->halo_after[2];
+    const u32 carry_in = st->carry_in;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int32_t *gdelta = delta + HDR_INTS;
+
+    if (n == 0)
+    {
+        if (blockIdx.x == 0 && tid == 0)
+            st->n_next = 0;
+        return;
+    }
+    if (SMEM_HIST)
+        for (u32 i = tid; i < 4 * (z + 1); i += R_THREADS)
+            s_hist[i] = 0;
+
+    for (;;)
+    {
+        __syncthreads();
+        if (tid == 0)
+            s_tile = atomicAdd(&st->ticket, 1u);
+        __syncthreads();
+        const u64 tile = s_tile;
+        if (tile >= ntiles)
+            break;
+        const u64 base = tile * R_TILE;
+        const u32 tl = (u32)((n - base < (u64)R_TILE) ? (n - base) : (u64)R_TILE);
+
+        // ---- stage the tile: s_tok[4 + p] = token at local position p, p in [-4, R_TILE + 4)
+        {
+            const uint4 *in4 = reinterpret_cast<const uint4 *>(in);
+            uint4 *s4 = reinterpret_cast<uint4 *>(s_tok);
+            for (int v = tid; v < R_TILE / 4 + 2; v += R_THREADS)
+            {
+                const i64 g0 = (i64)base + 4 * (i64)v - 4;
+                uint4 q;
+                if (g0 >= 0 && (u64)g0 + 4 <= n)
+                    q = __ldg(in4 + (g0 >> 2));
+                else
+                {
+                    u32 e[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                    {
+                        const i64 g = g0 + k;
+                        u32 val;
+                        if (g < 0)
+                            val = (g == -1) ? hb1 : ((g == -2) ? hb0 : SENT);
+                        else if ((u64)g < n)
+                            val = in[g];
+                        else
+                        {
+                            const u64 o = (u64)g - n;
+                            val = (o == 0) ? ha0 : ((o == 1) ? ha1 : ((o == 2) ? ha2 : SENT));
+                        }
+                        e[k] = val;
+                    }
+                    q = make_uint4(e[0], e[1], e[2], e[3]);
+                }
+                s4[v] = q;
+            }
+        }
+        __syncthreads();
+
+        // ---- my window: w[k] = token at local position p0 + k - 2
+        const u32 p0 = (u32)tid * R_ITEMS;
+        u32 w[R_ITEMS + 5];
+#pragma unroll
+        for (int k = 0; k < R_ITEMS + 5; k++)
+            w[k] = s_tok[p0 + k + 2];
+        const u32 valid = (p0 >= tl) ? 0u : ((tl - p0 < (u32)R_ITEMS) ? (tl - p0) : (u32)R_ITEMS);
+        const u32 vmask = (1u << valid) - 1u;
+        const u32 OWNV = vmask << 2;
+        u32 ea = 0, eb = 0;
+#pragma unroll
+        for (int k = 0; k < R_ITEMS + 5; k++)
+        {
+            ea |= (u32)(w[k] == a) << k;
+            eb |= (u32)(w[k] == b) << k;
+        }
+
+        u32 m; // bit k: a replacement starts at window index k
+        if (!same)
+            m = ea & (eb >> 1);
+        else
+        {
+            const int all_a = __syncthreads_and(((ea >> 2) & vmask) == vmask);
+            if (tid == 0)
+            {
+                u32 lp; // parity of the run of a that ends at the tile's last token
+                if (all_a)
+                    lp = tl & 1u;
+                else
+                {
+                    u32 c = 0;
+                    int i = (int)tl - 1;
+                    while (i >= 0 && s_tok[4 + i] == a)
+                    {
+                        c++;
+                        i--;
+                    }
+                    lp = c & 1u;
+                }
+                *reinterpret_cast<volatile u32 *>(pdesc + tile) = pd_pack(PD_LOCAL, epoch, (u32)all_a, lp);
+                u32 carry;
+                if (tile == 0)
+                    carry = carry_in;
+                else if (s_tok[3] != a)
+                    carry = 0;
+                else
+                {
+                    u32 acc = 0;
+                    i64 q = (i64)tile - 1;
+                    for (;;)
+                    {
+                        u32 d;
+                        do
+                        {
+                            d = *reinterpret_cast<volatile u32 *>(pdesc + q);
+                        } while ((d >> 30) == 0 || (d & 0x3FFFFFu) != (epoch & 0x3FFFFFu));
+                        const u32 par = (d >> 28) & 1u;
+                        if ((d >> 30) == 2u || !((d >> 29) & 1u))
+                        {
+                            carry = acc ^ par;
+                            break;
+                        }
+                        acc ^= par;
+                        if (q == 0)
+                        {
+                            carry = acc ^ carry_in;
+                            break;
+                        }
+                        q--;
+                    }
+                }
+                *reinterpret_cast<volatile u32 *>(pdesc + tile) =
+                    pd_pack(PD_RESOLVED, epoch, (u32)all_a, all_a ? (carry ^ (tl & 1u)) : lp);
+                s_carry = carry;
+            }
+            __syncthreads();
+            const u32 carry = s_carry;
+            u32 par0 = 0; // parity of the number of a right in front of my first token
+            if (valid > 0 && ((ea >> 1) & 1u))
+            {
+                if (p0 == 0)
+                    par0 = carry;
+                else
+                {
+                    u32 c = 0;
+                    int i = (int)p0 - 1;
+                    while (i >= 0 && s_tok[4 + i] == a)
+                    {
+                        c++;
+                        i--;
+                    }
+                    par0 = (i < 0) ? ((c ^ carry) & 1u) : (c & 1u);
+                }
+            }
+            m = ((ea >> 1) & (ea >> 2) & 1u & par0) << 1; // does one start at my left neighbour?
+            u32 par = par0;
+#pragma unroll
+            for (int k = 2; k < R_ITEMS + 2; k++)
+            {
+                const u32 isa = (ea >> k) & 1u;
+                m |= (isa & ((ea >> (k + 1)) & 1u) & (par ^ 1u)) << k;
+                par = isa ? (par ^ 1u) : 0u;
+            }
+        }
+        const u32 mm = m & OWNV;                 // replacements that start on my tokens
+        const u32 keep = OWNV & ~(m << 1);       // a token goes away iff one starts at its left neighbour
+        const u32 cnt = (u32)__popc(keep);
+
+        // ---- block-wide exclusive scan of the kept counts
+        u32 incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        if (lane == 31)
+            s_warp[warp] = incl;
+        __syncthreads(); // every thread has read its window: s_tok may now be overwritten
+        u32 woff = 0, total = 0;
+#pragma unroll
+        for (int i = 0; i < R_THREADS / 32; i++)
+        {
+            const u32 t = s_warp[i];
+            woff += (i < warp) ? t : 0u;
+            total += t;
+        }
+        if (tid == 0)
+            *reinterpret_cast<volatile u64 *>(desc + tile) = desc_pack(tile == 0 ? DESC_INCL : DESC_AGG, epoch, total);
+
+        // ---- compact into shared memory
+        u32 *s_out = s_tok + 4;
+        {
+            u32 r = woff + incl - cnt;
+#pragma unroll
+            for (int k = 2; k < R_ITEMS + 2; k++)
+                if ((keep >> k) & 1u)
+                    s_out[r++] = ((mm >> k) & 1u) ? z : w[k];
+        }
+
+        // ---- pair-count deltas
+        if (mm)
+        {
+#pragma unroll
+            for (int k = 2; k < R_ITEMS + 2; k++)
+                if ((mm >> k) & 1u)
+                {
+                    const u32 x = w[k - 1], y = w[k + 2];
+                    const u32 pm = same ? ((ea >> (k - 1)) & 1u) : ((m >> (k - 2)) & 1u);
+                    const u32 nm = (ea >> (k + 2)) & (eb >> (k + 3)) & 1u;
+                    if (x != SENT)
+                    {
+                        if (!(same && x == a))
+                        {
+                            if (SMEM_HIST)
+                                atomicAdd(&s_hist[x * 4 + 0], 1);
+                            else
+                                atomicAdd(&gdelta[(u64)x * 4 + 0], 1);
+                        }
+                        const u32 xn = pm ? z : x;
+                        if (SMEM_HIST)
+                            atomicAdd(&s_hist[xn * 4 + 2], 1);
+                        else
+                            atomicAdd(&gdelta[(u64)xn * 4 + 2], 1);
+                    }
+                    if (y != SENT && !nm)
+                    {
+                        if (!(same && y == a))
+                        {
+                            if (SMEM_HIST)
+                                atomicAdd(&s_hist[y * 4 + 1], 1);
+                            else
+                                atomicAdd(&gdelta[(u64)y * 4 + 1], 1);
+                        }
+                        if (SMEM_HIST)
+                            atomicAdd(&s_hist[y * 4 + 3], 1);
+                        else
+                            atomicAdd(&gdelta[(u64)y * 4 + 3], 1);
+                    }
+                }
+        }
+
+        // ---- decoupled look-back: where does this tile's output start?
+        if (warp == 0)
+        {
+            u64 excl = 0;
+            if (tile > 0)
+            {
+                i64 q = (i64)tile - 1 - lane;
+                for (;;)
+                {
+                    u64 d;
+                    bool ok;
+                    do
+                    {
+                        d = (q >= 0) ? *reinterpret_cast<volatile u64 *>(desc + q) : desc_pack(DESC_INCL, epoch, 0);
+                        ok = desc_ready(d, epoch);
+                    } while (!__all_sync(0xFFFFFFFFu, ok));
+                    const u32 incl_mask = __ballot_sync(0xFFFFFFFFu, (d >> 62) == 2ull);
+                    u64 c = d & DESC_COUNT_MASK;
+                    if (incl_mask && lane > (__ffs(incl_mask) - 1))
+                        c = 0;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1)
+                        c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+                    excl += c;
+                    if (incl_mask)
+                        break;
+                    q -= 32;
+                }
+                if (lane == 0)
+                    *reinterpret_cast<volatile u64 *>(desc + tile) = desc_pack(DESC_INCL, epoch, excl + total);
+            }
+            if (lane == 0)
+                s_excl = excl;
+        }
+        __syncthreads();
+        const u64 excl = s_excl;
+        for (u32 i = tid; i < total; i += R_THREADS)
+            out[excl + i] = s_out[i];
+        if (tile == ntiles - 1 && tid == 0)
+            st->n_next = excl + total;
+    }
+
+    if (SMEM_HIST)
+    {
+        // all threads left the loop through the same barrier pair; publish the privatised deltas
+        for (u32 i = tid; i < 4 * (z + 1); i += R_THREADS)
+        {
+            const int32_t v = s_hist[i];
+            if (v)
+                atomicAdd(&gdelta[i], v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: fold the (all-reduced) delta vectors into the replicated pair table, zero the merged pair,
+// keep D exact, flip the ping-pong buffers.
+__global__ void __launch_bounds__(256) apply_kernel(DevState *st, int32_t *delta_in, int32_t *delta_local)
+{
+    if (st->stop != STOP_RUN)
+        return;
+    const u32 gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (st->skip)
+        return;
+    const u32 a = st->a, b = st->b, z = st->z;
+    const u32 total = 4 * (z + 1);
+    u64 *tmeta = st->tmeta;
+    for (u32 i = gtid; i < total; i += gridDim.x * blockDim.x)
+    {
+        const int32_t d = delta_in[HDR_INTS + i];
+        if (delta_local != delta_in)
+            delta_local[HDR_INTS + i] = 0;
+        if (!d)
+            continue;
+        delta_in[HDR_INTS + i] = 0;
+        const u32 t = i >> 2, vec = i & 3u;
+        u32 ka, kb;
+        if (vec == 0)
+        {
+            ka = t;
+            kb = a;
+        }
+        else if (vec == 1)
+        {
+            ka = b;
+            kb = t;
+        }
+        else if (vec == 2)
+        {
+            ka = t;
+            kb = z;
+        }
+        else
+        {
+            ka = z;
+            kb = t;
+        }
+        const u64 key = (u64)ka | ((u64)kb << 32);
+        const u32 h = murmur3_pair(ka, kb);
+        if (vec >= 2)
+        {
+            const u64 s = table_insert(st, key, h);
+            if (s == NO_SLOT)
+            {
+                atomicOr(&st->err, ERR_TABLE_FULL);
+                continue;
+            }
+            const u32 old = atomicAdd(cnt_ptr(tmeta, s), (u32)d);
+            if (old == 0)
+                atomicAdd(reinterpret_cast<u64 *>(&st->distinct), 1ull);
+        }
+        else
+        {
+            const u64 s = table_find(st->tkey, st->tcap, key, h);
+            if (s == NO_SLOT)
+            {
+                atomicOr(&st->err, ERR_MISSING_KEY);
+                continue;
+            }
+            const u32 old = atomicSub(cnt_ptr(tmeta, s), (u32)d);
+            if (old < (u32)d)
+                atomicOr(&st->err, ERR_NEGATIVE);
+            if (old == (u32)d)
+                atomicAdd(reinterpret_cast<u64 *>(&st->distinct), ~0ull); // -1
+        }
+    }
+    if (gtid == 0)
+    {
+        const u64 s = table_find(st->tkey, st->tcap, (u64)a | ((u64)b << 32), murmur3_pair(a, b));
+        if (s != NO_SLOT)
+        {
+            const u32 old = atomicExch(cnt_ptr(tmeta, s), 0u); // the merged pair is gone
+            if (old)
+                atomicAdd(reinterpret_cast<u64 *>(&st->distinct), ~0ull);
+        }
+        st->n = st->n_next;
+        st->cur ^= 1u;
+    }
+}
+
+// halos of the untouched stream (before the first merge), for the shard-straddling byte pair
+__global__ void resolve_edges_kernel(DevState *st, const int32_t *delta_reduced)
+{
+    if (st->world > 1)
+        resolve_edges(st, reinterpret_cast<const u32 *>(delta_reduced), SENT, false);
+    else
+        st->n_global = st->n;
+}
+
+// host cleared a pause: resume the step sequence
+__global__ void resume_kernel(DevState *st)
+{
+    if (st->stop == STOP_PAUSE)
+    {
+        st->stop = STOP_RUN;
+        st->pause = 0;
+    }
+}
+
+// a skipped encode rank still has to advance (no pass, no deltas): nothing to do, the stream and
+// the table are unchanged.  Paused / finished steps fall through every kernel above.
+
+} // namespace bpe

@@ -1,0 +1,120 @@
+"""GPU suite (-m gpu): the CUDA engine, called through its C ABI, against the committed reference
+fixtures and the CPU oracle on the same seeded inputs.  Bit-exact: merge list, ids."""
+import numpy as np
+import pytest
+
+import oracle_api
+from oracle_api import FAST, FAST_CF
+
+pytestmark = pytest.mark.gpu
+
+
+def corpus(kind, size, seed):
+    from llmtokenizer_b200 import _lib
+    lib = _lib.load_corpus()
+    buf = np.zeros(size, dtype=np.uint8)
+    assert lib.gen_corpus_fill(kind, buf.ctypes.data, size, seed, 50000 if kind == 0 else 65536) == 0
+    return buf
+
+
+def assert_same(engine, oracle, data, cap=0, n_gpus=1, what=""):
+    rc, om, ot, ost = oracle.train(data, cap, FAST_CF)
+    assert rc == 0
+    m, t, st = engine.train(data, max_merges=cap, n_gpus=n_gpus)
+    k = min(len(m), len(om))
+    first_bad = next((i for i in range(k) if tuple(m[i]) != tuple(om[i])), None)
+    assert first_bad is None and len(m) == len(om), (
+        f"{what}: merge lists differ (engine {len(m)} merges, oracle {len(om)}, first mismatch at {first_bad}: "
+        f"engine {m[first_bad].tolist() if first_bad is not None else None} oracle "
+        f"{om[first_bad].tolist() if first_bad is not None else None}); engine stats {st}; oracle stats {ost}")
+    assert np.array_equal(t, ot), f"{what}: ids differ; engine stats {st}"
+    return m, t, st
+
+
+@pytest.mark.parametrize("name", oracle_api.golden_names())
+def test_reference_fixtures(engine, name):
+    g = oracle_api.golden(name)
+    if g["status"]:
+        with pytest.raises(engine.BpeCudaError) as e:
+            engine.train(g["input"], max_merges=g["cap"])
+        assert e.value.rc == -2      # "File contains less than 2 characters" (bpe.c:558-563)
+        return
+    m, t, st = engine.train(g["input"], max_merges=g["cap"])
+    k = min(len(m), len(g["merges"]))
+    first_bad = next((i for i in range(k) if tuple(m[i]) != tuple(g["merges"][i])), None)
+    assert first_bad is None and len(m) == len(g["merges"]), (name, len(m), len(g["merges"]), first_bad, st)
+    assert len(t) == g["n_ids"] and oracle_api.ids_sha(t) == g["ids_sha256"], (name, st)
+
+
+def test_random_small_inputs(engine, oracle):
+    rng = np.random.default_rng(17)
+    for case in range(60):
+        n = int(rng.integers(2, 4000))
+        kind = case % 4
+        if kind == 0:
+            data = rng.integers(97, 97 + int(rng.integers(1, 4)), n, dtype=np.uint8)
+        elif kind == 1:
+            data = rng.integers(32, 127, n, dtype=np.uint8)
+        elif kind == 2:
+            data = rng.integers(1, 256, n, dtype=np.uint8)
+        else:
+            data = np.repeat(rng.integers(97, 101, n // 3 + 1, dtype=np.uint8), rng.integers(1, 7, n // 3 + 1))[:n]
+        assert_same(engine, oracle, data, what=f"case {case} kind {kind} n {n}")
+
+
+@pytest.mark.parametrize("n", [3839, 3840, 3841, 7679, 7680, 7681, 3840 * 5 + 1, 3840 * 40 - 2])
+def test_tile_boundaries_and_runs(engine, oracle, n):
+    # tile size of the replace kernel is 3,840 tokens: streams that end on / around tile edges,
+    # made of long runs so that a == b merges and their run parity cross tiles
+    rng = np.random.default_rng(n)
+    runs = np.repeat(rng.integers(97, 100, n, dtype=np.uint8), rng.integers(1, 40, n))[:n]
+    assert_same(engine, oracle, runs, cap=40, what=f"runs n={n}")
+    allsame = np.full(n, 97, dtype=np.uint8)
+    assert_same(engine, oracle, allsame, what=f"all-a n={n}")
+    ab = np.tile(np.frombuffer(b"ab", dtype=np.uint8), n // 2 + 1)[:n]
+    assert_same(engine, oracle, ab, what=f"abab n={n}")
+
+
+def test_medium_corpora_capped(engine, oracle):
+    assert_same(engine, oracle, corpus(0, 6_000_000, 99), cap=300, what="zipf_ascii 6 MB / 300 merges")
+    assert_same(engine, oracle, corpus(1, 5_000_000, 98), cap=150, what="zipf_bytes 5 MB / 150 merges")
+    rt = oracle_api.golden("rt_full_cap300")["input"]
+    big = np.concatenate([rt, rt[::-1], rt[:300000]])      # 2.4 M tokens, dynamic regime throughout
+    assert_same(engine, oracle, big, cap=120, what="2.4 MB random text / 120 merges")
+
+
+def test_encode_matches_training_ids_and_oracle(engine, oracle):
+    data = corpus(0, 1_500_000, 5)
+    m, t, _ = engine.train(data, max_merges=400)
+    ids, st = engine.encode(data, m)
+    assert np.array_equal(ids, t), "encoding the training text with its own merges must reproduce compress()'s ids"
+    other = corpus(0, 700_000, 6)
+    ids2, st2 = engine.encode(other, m)
+    assert np.array_equal(ids2, oracle.encode(other, m))
+    assert oracle.decode(ids2, m) == other.tobytes()
+    assert st2["ranks_applied"] <= 400
+
+
+def test_nul_truncation_and_unsigned_bytes(engine, oracle):
+    data = np.frombuffer(b"abab\0abababab", dtype=np.uint8)
+    m, t, _ = engine.train(data)
+    assert m.tolist() == [[97, 98]] and t.tolist() == [256, 256]
+    hi = np.frombuffer(bytes.fromhex("fffefffefffe"), dtype=np.uint8)
+    m, t, _ = engine.train(hi)
+    assert m.tolist() == [[255, 254], [256, 256]] and t.tolist() == [257, 256]  # k9
+
+
+def test_repeated_calls_and_context_reuse(engine, oracle):
+    # the reference's compress() can be called once per process; the engine must not care
+    data = corpus(0, 300_000, 1)
+    ctx = engine.Context(0)
+    ctx.upload(data)
+    outs = []
+    for _ in range(3):
+        ctx.train(50)
+        outs.append(ctx.download())
+    ctx.close()
+    for m, t in outs[1:]:
+        assert np.array_equal(m, outs[0][0]) and np.array_equal(t, outs[0][1])
+    rc, om, ot, _ = oracle.train(data, 50, FAST)
+    assert np.array_equal(outs[0][0], om) and np.array_equal(outs[0][1], ot)
