@@ -59,6 +59,7 @@ typedef struct
     double ms_device;          /* CUDA-event time of the whole run on this rank's stream           */
     double ms_h2d, ms_d2h;     /* host<->device copies (host-buffer entry points only)             */
     double ms_total;           /* wall clock of the call                                           */
+    uint64_t worker_buckets[16]; /* emulated bucket counts of the reference's 16 worker tables      */
 } bpe_cuda_stats_t;
 
 #define BPE_CUDA_OK 0

@@ -16,10 +16,13 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "n_input", "n_merges", "n_tokens", "ranks_applied", "same_bucket_ties", "threshold_edges", "resolver_runs",
         "census_runs", "table_rehashes", "table_capacity", "final_distinct", "kernel_launches", "replace_launches",
-        "replace_bytes")] + [(n, C.c_double) for n in ("replace_ms", "ms_device", "ms_h2d", "ms_d2h", "ms_total")]
+        "replace_bytes")] + [(n, C.c_double) for n in ("replace_ms", "ms_device", "ms_h2d", "ms_d2h", "ms_total")] + [
+        ("worker_buckets", C.c_uint64 * 16)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        d = {n: getattr(self, n) for n, _ in self._fields_[:-1]}
+        d["worker_buckets"] = list(self.worker_buckets)
+        return d
 
 
 EXPORTS = [

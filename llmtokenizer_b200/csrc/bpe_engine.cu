@@ -8,6 +8,7 @@
 // There is no CPU fallback anywhere in this file: without a CUDA device every entry point fails.
 #include "../../include/bpe_cuda.h"
 #include "bpe_kernels.cuh"
+#include "bpe_resolver.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -138,6 +139,16 @@ struct bpe_cuda_ctx
     SelPart *d_part = nullptr;
     int sel_grid = 0;
     u32 *d_dense = nullptr;
+    // exact tie-break machinery (bpe_resolver.cuh)
+    ResState *d_rs = nullptr;
+    u64 *d_first = nullptr;
+    u32 *d_rank = nullptr;
+    size_t first_cap = 0; // entries (slots * slices)
+    u32 *d_pos_slot = nullptr;
+    size_t pos_cap = 0;
+    u32 *d_tile_cnt = nullptr;
+    u64 *d_tile_off = nullptr;
+    size_t tile_cap = 0;
     // communicator
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
@@ -325,8 +336,69 @@ static int setup_kernels(bpe_cuda_ctx *c)
     return 0;
 }
 
+// scratch of the census / resolver: first position and first-sight rank per (table slot, slice),
+// table slot per stream position, scan scratch.  Stamped with a census epoch, never cleared.
+static int ensure_resolver(bpe_cuda_ctx *c, u64 n, u32 slices)
+{
+    if (!c->d_rs)
+    {
+        CU(cudaMalloc(&c->d_rs, sizeof(ResState)));
+        CU(cudaMemsetAsync(c->d_rs, 0, sizeof(ResState), c->stream));
+    }
+    const size_t ent = (size_t)c->tcap * slices;
+    if (ent > c->first_cap)
+    {
+        if (c->d_first)
+            CU(cudaFree(c->d_first));
+        if (c->d_rank)
+            CU(cudaFree(c->d_rank));
+        c->d_first = nullptr;
+        c->d_rank = nullptr;
+        CU(cudaMalloc(&c->d_first, ent * sizeof(u64)));
+        CU(cudaMalloc(&c->d_rank, ent * sizeof(u32)));
+        CU(cudaMemsetAsync(c->d_first, 0, ent * sizeof(u64), c->stream));
+        c->first_cap = ent;
+    }
+    if (n + 16 > c->pos_cap)
+    {
+        if (c->d_pos_slot)
+            CU(cudaFree(c->d_pos_slot));
+        c->d_pos_slot = nullptr;
+        CU(cudaMalloc(&c->d_pos_slot, (n + 16) * sizeof(u32)));
+        c->pos_cap = n + 16;
+    }
+    const size_t tiles = n / SCAN_TILE + 2;
+    if (tiles > c->tile_cap)
+    {
+        if (c->d_tile_cnt)
+            CU(cudaFree(c->d_tile_cnt));
+        if (c->d_tile_off)
+            CU(cudaFree(c->d_tile_off));
+        c->d_tile_cnt = nullptr;
+        c->d_tile_off = nullptr;
+        CU(cudaMalloc(&c->d_tile_cnt, tiles * sizeof(u32)));
+        CU(cudaMalloc(&c->d_tile_off, tiles * sizeof(u64)));
+        c->tile_cap = tiles;
+    }
+    return 0;
+}
+
+static int pos_grid(bpe_cuda_ctx *c, u64 n) { return (int)std::max<u64>(1, std::min<u64>((n + 255) / 256, (u64)c->sm_count * 8)); }
+
+// the 16-slice distinct-pair census that keeps the worker tables' bucket counts exact
+static int enqueue_census(bpe_cuda_ctx *c, u64 n_upper, int resolver)
+{
+    const int g = pos_grid(c, n_upper);
+    census_begin_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_rs, resolver, c->force_census);
+    census_mark_kernel<<<g, 256, 0, c->stream>>>(c->d_st, c->d_rs, c->d_first, c->d_pos_slot);
+    census_count_kernel<<<g, 256, 0, c->stream>>>(c->d_st, c->d_rs, c->d_first, c->d_pos_slot);
+    census_update_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_rs);
+    c->launches += 4;
+    return 0;
+}
+
 // enqueue one merge step; z is the id the step will create if it runs
-static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool with_select)
+static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool with_select, bool census = false)
 {
     if (with_select)
     {
@@ -335,6 +407,13 @@ static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool w
         else
             select_kernel<<<c->sel_grid, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_part, c->d_delta_red);
         c->launches++;
+        if (census)
+        {
+            int rc = enqueue_census(c, n_upper, 0);
+            if (rc)
+                return rc;
+            c->stats.census_runs++;
+        }
     }
     const bool hist = ((int)z + 1 <= c->smem_hist_max_vocab);
     const size_t smem = replace_smem_bytes(hist, z);
@@ -415,8 +494,25 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
             return rc;
         if ((rc = ensure_logs(c, (size_t)(m0 + G + 1))))
             return rc;
+        // Worker-table growth is only possible while some slice can still hold thr(B_t) distinct pairs.
+        bool census = false;
+        if (!encode && c->world == 1)
+        {
+            const bool stat = h->n < STATIC_LIMIT;
+            if (c->force_census)
+                census = true;
+            else if (stat)
+            {
+                const u64 dmax = (u64)h->distinct + margin;
+                for (int t = 0; t < REF_THREADS; t++)
+                    if (std::min<u64>(h->n / REF_THREADS + 32, dmax) >= resize_threshold(h->bt[t]))
+                        census = true;
+            }
+            if (census && (rc = ensure_resolver(c, h->n, stat ? REF_THREADS : 1)))
+                return rc;
+        }
         for (u64 g = 0; g < G; g++)
-            if ((rc = enqueue_step(c, (u32)(z0 + g), h->n, encode, true)))
+            if ((rc = enqueue_step(c, (u32)(z0 + g), h->n, encode, true, census)))
                 return rc;
         CU(cudaGetLastError());
         if ((rc = poll_state(c)))
@@ -603,6 +699,8 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
     c->stats.final_distinct = (u64)h->distinct;
     c->stats.kernel_launches = c->launches;
     c->stats.ms_device = ms;
+    for (int t = 0; t < REF_THREADS; t++)
+        c->stats.worker_buckets[t] = h->bt[t];
     // algorithmic bytes of the replace passes: 4*(n_k + n_{k+1}) per merge that ran a pass
     if (h->merges_done)
     {
@@ -664,8 +762,32 @@ static int resolve_pause(bpe_cuda_ctx *c, bool encode)
         return rc;
     if ((rc = ensure_logs(c, (size_t)(h->merges_done + 2))))
         return rc;
-    tier_a_commit_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_delta_red);
-    c->launches++;
+    if (c->world > 1)
+    {
+        // sharded stream: chain order is taken from the table order (documented limitation; counted)
+        tier_a_commit_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_delta_red);
+        c->launches++;
+        return enqueue_step(c, (u32)(256 + h->merges_done), h->n, encode, false);
+    }
+    const u32 slices = (h->n < STATIC_LIMIT) ? REF_THREADS : 1;
+    if ((rc = ensure_resolver(c, h->n, slices)))
+        return rc;
+    if ((rc = enqueue_census(c, h->n, 1)))
+        return rc;
+    const int g = pos_grid(c, h->n);
+    const int tg = (int)std::max<u64>(1, std::min<u64>(h->n / SCAN_TILE + 1, (u64)c->sm_count * 8));
+    const int sg = (int)std::min<u64>((c->tcap + 255) / 256, (u64)c->sm_count * 8);
+    rank_tile_count_kernel<<<tg, 256, 0, c->stream>>>(c->d_rs, c->d_first, c->d_pos_slot, c->d_tile_cnt);
+    rank_tile_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_rs, c->d_tile_cnt, c->d_tile_off);
+    rank_assign_kernel<<<tg, 256, 0, c->stream>>>(c->d_rs, c->d_first, c->d_pos_slot, c->d_tile_off, c->d_rank);
+    entry_pass1_kernel<<<g, 256, 0, c->stream>>>(c->d_st, c->d_rs, c->d_first, c->d_pos_slot, c->d_rank);
+    resolver_mid_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_rs);
+    cand_bucket_kernel<<<sg, 256, 0, c->stream>>>(c->d_st, c->d_rs);
+    cand_collect_kernel<<<sg, 256, 0, c->stream>>>(c->d_st, c->d_rs, c->d_first, c->d_rank);
+    entry_pass2_kernel<<<g, 256, 0, c->stream>>>(c->d_st, c->d_rs, c->d_first, c->d_pos_slot, c->d_rank);
+    resolver_commit_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_rs, c->d_delta_red);
+    c->launches += 9;
+    CU(cudaGetLastError());
     return enqueue_step(c, (u32)(256 + h->merges_done), h->n, encode, false);
 }
 
@@ -760,6 +882,12 @@ void bpe_cuda_ctx_destroy(bpe_cuda_ctx_t *c)
     cudaFree(c->d_enc_merges);
     cudaFree(c->d_part);
     cudaFree(c->d_dense);
+    cudaFree(c->d_rs);
+    cudaFree(c->d_first);
+    cudaFree(c->d_rank);
+    cudaFree(c->d_pos_slot);
+    cudaFree(c->d_tile_cnt);
+    cudaFree(c->d_tile_off);
     if (c->stream)
         cudaStreamDestroy(c->stream);
     delete c;

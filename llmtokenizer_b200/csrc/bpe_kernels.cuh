@@ -533,8 +533,42 @@ __device__ __forceinline__ void sel_block_reduce(u64 &k, u64 &s, u32 &m, SelPart
     }
 }
 
+// Above 1,048,576 tokens the canonical schedule gives every chunk to worker 0: its
+// table sees all D keys, and its last insert call creates a key iff the stream's last pair occurs
+// exactly once.  That keeps the worker's persistent bucket count exact without touching the stream.
+__device__ inline void dynamic_regime_census(DevState *st, const u32 *rec_all)
+{
+    u32 x = SENT, y = SENT;
+    if (st->world > 1)
+    {
+        int got = 0;
+        u32 last2[2] = {SENT, SENT};
+        for (int q = (int)st->world - 1; q >= 0 && got < 2; q--)
+        {
+            const u32 *rc = rec_all + q * REC_INTS;
+            const u64 len = (u64)rc[0] | ((u64)rc[1] << 32);
+            if (len >= 1 && got < 2)
+                last2[1 - got++] = rc[6];
+            if (len >= 2 && got < 2)
+                last2[1 - got++] = rc[5];
+        }
+        x = last2[0];
+        y = last2[1];
+    }
+    else if (st->n >= 2)
+    {
+        x = st->tok[st->cur][st->n - 2];
+        y = st->tok[st->cur][st->n - 1];
+    }
+    if (x == SENT || y == SENT)
+        return;
+    const u64 s = table_find(st->tkey, st->tcap, (u64)x | ((u64)y << 32), murmur3_pair(x, y));
+    const bool last_new = (s != NO_SLOT) && (*cnt_ptr(st->tmeta, s) == 1u);
+    st->bt[0] = grown_buckets(st->bt[0], (u64)st->distinct, last_new);
+}
+
 // record the chosen pair and prepare the pass (single thread)
-__device__ inline void commit_merge(DevState *st, u32 a, u32 b, u32 freq, const u32 *rec_all)
+__device__ inline void commit_merge(DevState *st, u32 a, u32 b, u32 freq, const u32 *rec_all, bool encode = false)
 {
     const u64 k = st->merges_done;
     st->a = a;
@@ -548,6 +582,8 @@ __device__ inline void commit_merge(DevState *st, u32 a, u32 b, u32 freq, const 
         resolve_edges(st, rec_all, a, a == b);
     else
         st->n_global = st->n;
+    if (!encode && st->n_global >= STATIC_LIMIT)
+        dynamic_regime_census(st, rec_all);
     st->n_hist[k] = st->n_global;
     st->merges_done = k + 1;
     st->epoch = st->epoch + 1;
@@ -661,7 +697,7 @@ __global__ void select_rank_kernel(DevState *st, const int32_t *delta_reduced)
     const u64 slot = table_find(st->tkey, st->tcap, (u64)a | ((u64)b << 32), murmur3_pair(a, b));
     const u32 cnt = (slot == NO_SLOT) ? 0u : *cnt_ptr(st->tmeta, slot);
     const u32 *rec_all = reinterpret_cast<const u32 *>(delta_reduced);
-    commit_merge(st, a, b, cnt, rec_all);
+    commit_merge(st, a, b, cnt, rec_all, true);
     if (cnt == 0)
         st->skip = 1;
     else

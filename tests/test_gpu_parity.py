@@ -28,6 +28,10 @@ def assert_same(engine, oracle, data, cap=0, n_gpus=1, what=""):
         f"engine {m[first_bad].tolist() if first_bad is not None else None} oracle "
         f"{om[first_bad].tolist() if first_bad is not None else None}); engine stats {st}; oracle stats {ost}")
     assert np.array_equal(t, ot), f"{what}: ids differ; engine stats {st}"
+    if n_gpus == 1:
+        # the emulated bucket counts of the reference's 16 worker tables must track the oracle's exactly
+        assert st["worker_buckets"] == ost["thread_buckets"], (what, st["worker_buckets"], ost["thread_buckets"])
+        assert st["same_bucket_ties"] == ost["same_bucket_ties"] and st["threshold_edges"] == ost["threshold_edges"]
     return m, t, st
 
 
