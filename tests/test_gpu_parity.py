@@ -122,3 +122,31 @@ def test_repeated_calls_and_context_reuse(engine, oracle):
         assert np.array_equal(m, outs[0][0]) and np.array_equal(t, outs[0][1])
     rc, om, ot, _ = oracle.train(data, 50, FAST)
     assert np.array_equal(outs[0][0], om) and np.array_equal(outs[0][1], ot)
+
+
+def _device_count():
+    from llmtokenizer_b200 import _lib
+    return _lib.load().bpe_cuda_device_count()
+
+
+@pytest.mark.parametrize("P", [2, 4, 8])
+def test_sharded_training_and_encoding_match_oracle(engine, oracle, P):
+    """Corpus sharded over P GPUs (one NCCL all-reduce of the delta vectors + edge records per merge) must give
+    exactly the single-stream result: merges, ids, any P."""
+    if _device_count() < P:
+        pytest.skip(f"needs {P} GPUs")
+    assert_same(engine, oracle, corpus(0, 8_000_000, 7), cap=200, n_gpus=P, what=f"zipf_ascii 8 MB P={P}")
+    assert_same(engine, oracle, corpus(1, 6_000_000, 8), cap=100, n_gpus=P, what=f"zipf_bytes 6 MB P={P}")
+    # long runs of equal bytes: a == b merges whose run parity crosses shard boundaries
+    rng = np.random.default_rng(P)
+    runs = np.repeat(rng.integers(97, 100, 400_000, dtype=np.uint8), rng.integers(1, 30, 400_000))[:4_000_001]
+    assert_same(engine, oracle, runs, cap=12, n_gpus=P, what=f"runs P={P}")
+    same = np.full(3_000_003, 120, dtype=np.uint8)
+    assert_same(engine, oracle, same, cap=1, n_gpus=P, what=f"single run P={P}")
+    data = corpus(0, 3_000_000, 9)
+    m, t, _ = engine.train(data, max_merges=300)
+    ids, _ = engine.encode(data, m, n_gpus=P)
+    assert np.array_equal(ids, t)
+    other = corpus(0, 2_000_001, 10)
+    ids2, _ = engine.encode(other, m, n_gpus=P)
+    assert np.array_equal(ids2, oracle.encode(other, m))
