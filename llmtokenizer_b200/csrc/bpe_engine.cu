@@ -126,17 +126,18 @@ struct bpe_cuda_ctx
     // delta vectors (+ edge-record header)
     int32_t *d_delta = nullptr, *d_delta_red = nullptr;
     size_t delta_cap = 0;
-    // pair table
+    // pair table (+ per-segment maxima of the hierarchical argmax)
     u64 *d_tkey = nullptr, *d_tmeta = nullptr;
     u64 tcap = 0;
+    SelPart *d_seg = nullptr;
+    u32 *d_seg_flag = nullptr, *d_seg_list = nullptr;
     // logs
     u32 *d_merges = nullptr;
     u64 *d_nhist = nullptr;
     size_t merges_cap = 0;
     u32 *d_enc_merges = nullptr;
     size_t enc_cap = 0;
-    // selection partials / dense byte-pair histogram
-    SelPart *d_part = nullptr;
+    // dense byte-pair histogram
     int sel_grid = 0;
     u32 *d_dense = nullptr;
     // exact tie-break machinery (bpe_resolver.cuh)
@@ -275,32 +276,63 @@ static int ensure_logs(bpe_cuda_ctx *c, size_t merges)
     return 0;
 }
 
-static int table_alloc(bpe_cuda_ctx *c, u64 cap, u64 **key, u64 **meta)
+struct TableMem
 {
-    CU(cudaMalloc(key, cap * sizeof(u64)));
-    CU(cudaMalloc(meta, cap * sizeof(u64)));
-    CU(cudaMemsetAsync(*key, 0xFF, cap * sizeof(u64), c->stream));
-    CU(cudaMemsetAsync(*meta, 0, cap * sizeof(u64), c->stream));
+    u64 *key = nullptr, *meta = nullptr;
+    SelPart *seg = nullptr;
+    u32 *seg_flag = nullptr, *seg_list = nullptr;
+};
+
+static int table_alloc(bpe_cuda_ctx *c, u64 cap, TableMem *t)
+{
+    const u64 nseg = cap >> SEG_SHIFT;
+    CU(cudaMalloc(&t->key, cap * sizeof(u64)));
+    CU(cudaMalloc(&t->meta, cap * sizeof(u64)));
+    CU(cudaMalloc(&t->seg, nseg * sizeof(SelPart)));
+    CU(cudaMalloc(&t->seg_flag, nseg * sizeof(u32)));
+    CU(cudaMalloc(&t->seg_list, nseg * sizeof(u32)));
+    CU(cudaMemsetAsync(t->key, 0xFF, cap * sizeof(u64), c->stream));
+    CU(cudaMemsetAsync(t->meta, 0, cap * sizeof(u64), c->stream));
+    CU(cudaMemsetAsync(t->seg_flag, 0, nseg * sizeof(u32), c->stream));
     return 0;
+}
+
+static void table_free(bpe_cuda_ctx *c)
+{
+    cudaFree(c->d_tkey);
+    cudaFree(c->d_tmeta);
+    cudaFree(c->d_seg);
+    cudaFree(c->d_seg_flag);
+    cudaFree(c->d_seg_list);
+    c->d_tkey = c->d_tmeta = nullptr;
+    c->d_seg = nullptr;
+    c->d_seg_flag = c->d_seg_list = nullptr;
+}
+
+static void table_adopt(bpe_cuda_ctx *c, const TableMem &t, u64 cap)
+{
+    c->d_tkey = t.key;
+    c->d_tmeta = t.meta;
+    c->d_seg = t.seg;
+    c->d_seg_flag = t.seg_flag;
+    c->d_seg_list = t.seg_list;
+    c->tcap = cap;
 }
 
 static int table_rehash(bpe_cuda_ctx *c, u64 new_cap)
 {
-    u64 *nk = nullptr, *nm = nullptr;
-    int rc = table_alloc(c, new_cap, &nk, &nm);
+    TableMem t;
+    int rc = table_alloc(c, new_cap, &t);
     if (rc)
         return rc;
     const int grid = (int)std::min<u64>((c->tcap + 255) / 256, (u64)c->sm_count * 8);
-    rehash_kernel<<<grid, 256, 0, c->stream>>>(c->d_tkey, c->d_tmeta, c->tcap, nk, nm, new_cap, &c->d_st->err);
-    table_swap_kernel<<<1, 1, 0, c->stream>>>(c->d_st, nk, nm, new_cap);
+    rehash_kernel<<<grid, 256, 0, c->stream>>>(c->d_tkey, c->d_tmeta, c->tcap, t.key, t.meta, new_cap, &c->d_st->err);
+    table_swap_kernel<<<1, 1, 0, c->stream>>>(c->d_st, t.key, t.meta, new_cap, t.seg, t.seg_flag, t.seg_list);
     c->launches += 2;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
-    CU(cudaFree(c->d_tkey));
-    CU(cudaFree(c->d_tmeta));
-    c->d_tkey = nk;
-    c->d_tmeta = nm;
-    c->tcap = new_cap;
+    table_free(c);
+    table_adopt(c, t, new_cap);
     c->stats.table_rehashes++;
     return 0;
 }
@@ -405,7 +437,7 @@ static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool w
         if (encode)
             select_rank_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_delta_red);
         else
-            select_kernel<<<c->sel_grid, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_part, c->d_delta_red);
+            select_kernel<<<c->sel_grid, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_delta_red);
         c->launches++;
         if (census)
         {
@@ -536,6 +568,11 @@ static int init_state(bpe_cuda_ctx *c, u64 n_local, u64 max_merges, bool encode,
     s.tkey = c->d_tkey;
     s.tmeta = c->d_tmeta;
     s.tcap = c->tcap;
+    s.seg = c->d_seg;
+    s.seg_flag = c->d_seg_flag;
+    s.seg_list = c->d_seg_list;
+    s.nseg = c->tcap >> SEG_SHIFT;
+    s.all_dirty = 1;
     s.halo_before[0] = s.halo_before[1] = SENT;
     s.halo_after[0] = s.halo_after[1] = s.halo_after[2] = SENT;
     s.rank = (u32)c->rank;
@@ -571,21 +608,15 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
         return rc;
     if (!c->d_dense)
         CU(cudaMalloc(&c->d_dense, 65536 * sizeof(u32)));
-    if (!c->d_part)
-    {
-        c->sel_grid = c->sm_count * 2;
-        CU(cudaMalloc(&c->d_part, (size_t)c->sel_grid * sizeof(SelPart)));
-    }
+    c->sel_grid = c->sm_count * 2;
     // fresh table
-    if (c->d_tkey)
+    table_free(c);
     {
-        CU(cudaFree(c->d_tkey));
-        CU(cudaFree(c->d_tmeta));
-        c->d_tkey = c->d_tmeta = nullptr;
+        TableMem t;
+        if ((rc = table_alloc(c, 1ull << 20, &t)))
+            return rc;
+        table_adopt(c, t, 1ull << 20);
     }
-    c->tcap = 1ull << 20;
-    if ((rc = table_alloc(c, c->tcap, &c->d_tkey, &c->d_tmeta)))
-        return rc;
     if (c->merges_cap == 0)
     {
         c->merges_cap = 8192;
@@ -875,12 +906,10 @@ void bpe_cuda_ctx_destroy(bpe_cuda_ctx_t *c)
     cudaFree(c->d_delta);
     if (c->d_delta_red != c->d_delta)
         cudaFree(c->d_delta_red);
-    cudaFree(c->d_tkey);
-    cudaFree(c->d_tmeta);
+    table_free(c);
     cudaFree(c->d_merges);
     cudaFree(c->d_nhist);
     cudaFree(c->d_enc_merges);
-    cudaFree(c->d_part);
     cudaFree(c->d_dense);
     cudaFree(c->d_rs);
     cudaFree(c->d_first);

@@ -53,6 +53,7 @@ enum : u32
 
 // Device-resident control block.  Everything a merge step needs lives here, so a step is a fixed
 // sequence of launches with no host round trip.
+struct SelPart;
 struct DevState
 {
     // token stream, ping-pong (pointers are 16 B aligned; 4 readable slots in front of each)
@@ -74,6 +75,14 @@ struct DevState
     u64 tcap;
     i64 distinct; // D: keys with count > 0
     u64 occupied; // claimed slots (dead keys included)
+    // segment maxima over the table (hierarchical argmax): only segments touched since the last
+    // selection are rescanned
+    struct SelPart *seg;
+    u32 *seg_flag;
+    u32 *seg_list;
+    u64 nseg;
+    u64 sel_B; // bucket count the segment maxima were computed for
+    u32 n_dirty, all_dirty;
     // scheduling counters
     u32 ticket, sel_done;
     // selection result (kept for the resolver)
@@ -340,12 +349,18 @@ __global__ void rehash_kernel(const u64 *__restrict__ okey, const u64 *__restric
     }
 }
 
-__global__ void table_swap_kernel(DevState *st, u64 *nkey, u64 *nmeta, u64 ncap)
+__global__ void table_swap_kernel(DevState *st, u64 *nkey, u64 *nmeta, u64 ncap, SelPart *seg, u32 *seg_flag, u32 *seg_list)
 {
     st->tkey = nkey;
     st->tmeta = nmeta;
     st->tcap = ncap;
     st->occupied = (u64)st->distinct;
+    st->seg = seg;
+    st->seg_flag = seg_flag;
+    st->seg_list = seg_list;
+    st->nseg = ncap >> 10;
+    st->n_dirty = 0;
+    st->all_dirty = 1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -591,35 +606,62 @@ __device__ inline void commit_merge(DevState *st, u32 a, u32 b, u32 freq, const 
 }
 
 constexpr int SEL_THREADS = 512;
+constexpr int SEG_SHIFT = 10; // 1,024 slots (8 KB of meta) per segment
+constexpr u64 SEG_SLOTS = 1ull << SEG_SHIFT;
 
-__global__ void __launch_bounds__(SEL_THREADS) select_kernel(DevState *st, SelPart *part, const int32_t *delta_reduced)
+__device__ __forceinline__ void mark_dirty(DevState *st, u64 slot)
+{
+    const u32 seg = (u32)(slot >> SEG_SHIFT);
+    if (atomicExch(&st->seg_flag[seg], 1u) == 0u)
+        st->seg_list[atomicAdd(&st->n_dirty, 1u)] = seg;
+}
+
+// Phase 1 (all blocks): recompute the maximum of every segment of the table that the last merge
+// touched (all of them when the bucket count B(D) changed or the table was rebuilt).
+// Phase 2 (last block to finish): fold the per-segment maxima and decide.
+__global__ void __launch_bounds__(SEL_THREADS) select_kernel(DevState *st, const int32_t *delta_reduced)
 {
     if (st->stop != STOP_RUN)
         return;
     __shared__ SelPart sm[SEL_THREADS / 32];
     __shared__ bool s_last;
-    const u64 cap = st->tcap;
     const u64 *__restrict__ meta = st->tmeta;
     const u64 D = (u64)st->distinct;
     const u64 B = merged_buckets(D);
     const u32 bmask = (u32)(B - 1);
-    u64 k = 0, s = NO_SLOT;
-    u32 m = 0;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x)
+    SelPart *segp = st->seg;
+    const u64 nseg = st->nseg;
+    const bool all = st->all_dirty || (B != st->sel_B);
+    const u64 nwork = all ? nseg : (u64)st->n_dirty;
+    u64 k, s;
+    u32 m;
+    for (u64 w = blockIdx.x; w < nwork; w += gridDim.x)
     {
-        const u64 mv = meta[i];
-        if (mv >> 32)
+        const u64 seg = all ? w : (u64)st->seg_list[w];
+        k = 0;
+        s = NO_SLOT;
+        m = 0;
+        for (u32 j = threadIdx.x; j < SEG_SLOTS; j += SEL_THREADS)
         {
-            const u64 kk = (mv & 0xFFFFFFFF00000000ull) | (u64)(0xFFFFFFFFu - ((u32)mv & bmask));
-            sel_combine(k, s, m, kk, i, 1u);
+            const u64 i = (seg << SEG_SHIFT) + j;
+            const u64 mv = meta[i];
+            if (mv >> 32)
+            {
+                const u64 kk = (mv & 0xFFFFFFFF00000000ull) | (u64)(0xFFFFFFFFu - ((u32)mv & bmask));
+                sel_combine(k, s, m, kk, i, 1u);
+            }
+        }
+        sel_block_reduce(k, s, m, sm);
+        if (threadIdx.x == 0)
+        {
+            segp[seg].key = k;
+            segp[seg].slot = s;
+            segp[seg].mult = m;
+            st->seg_flag[seg] = 0;
         }
     }
-    sel_block_reduce(k, s, m, sm);
     if (threadIdx.x == 0)
     {
-        part[blockIdx.x].key = k;
-        part[blockIdx.x].slot = s;
-        part[blockIdx.x].mult = m;
         __threadfence();
         const u32 done = atomicAdd(&st->sel_done, 1u);
         s_last = (done == gridDim.x - 1);
@@ -631,15 +673,18 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(DevState *st, SelPa
     k = 0;
     s = NO_SLOT;
     m = 0;
-    for (u32 i = threadIdx.x; i < gridDim.x; i += blockDim.x)
+    for (u64 i = threadIdx.x; i < nseg; i += blockDim.x)
     {
-        const volatile SelPart *p = part + i;
+        const volatile SelPart *p = segp + i;
         sel_combine(k, s, m, p->key, p->slot, p->mult);
     }
     sel_block_reduce(k, s, m, sm);
     if (threadIdx.x != 0)
         return;
     st->sel_done = 0;
+    st->n_dirty = 0;
+    st->all_dirty = 0;
+    st->sel_B = B;
     st->sel_key = k;
     st->sel_slot = s;
     st->sel_mult = m;
@@ -1126,6 +1171,7 @@ __global__ void __launch_bounds__(256) apply_kernel(DevState *st, int32_t *delta
             const u32 old = atomicAdd(cnt_ptr(tmeta, s), (u32)d);
             if (old == 0)
                 atomicAdd(reinterpret_cast<u64 *>(&st->distinct), 1ull);
+            mark_dirty(st, s);
         }
         else
         {
@@ -1140,6 +1186,7 @@ __global__ void __launch_bounds__(256) apply_kernel(DevState *st, int32_t *delta
                 atomicOr(&st->err, ERR_NEGATIVE);
             if (old == (u32)d)
                 atomicAdd(reinterpret_cast<u64 *>(&st->distinct), ~0ull); // -1
+            mark_dirty(st, s);
         }
     }
     if (gtid == 0)
@@ -1150,6 +1197,7 @@ __global__ void __launch_bounds__(256) apply_kernel(DevState *st, int32_t *delta
             const u32 old = atomicExch(cnt_ptr(tmeta, s), 0u); // the merged pair is gone
             if (old)
                 atomicAdd(reinterpret_cast<u64 *>(&st->distinct), ~0ull);
+            mark_dirty(st, s);
         }
         st->n = st->n_next;
         st->cur ^= 1u;
