@@ -60,6 +60,8 @@ typedef struct
     double ms_h2d, ms_d2h;     /* host<->device copies (host-buffer entry points only)             */
     double ms_total;           /* wall clock of the call                                           */
     uint64_t worker_buckets[16]; /* emulated bucket counts of the reference's 16 worker tables      */
+    /* only when profiling is enabled: device time of the other step kernels and of host-induced gaps */
+    double select_ms, apply_ms, gap_ms;
 } bpe_cuda_stats_t;
 
 #define BPE_CUDA_OK 0

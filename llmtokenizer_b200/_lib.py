@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libbpe_cuda.so")
+LIB_PATH = os.environ.get("BPE_CUDA_LIB") or os.path.join(PKG, "libbpe_cuda.so")  # override: A/B builds of the kernels
 CORPUS_LIB_PATH = os.path.join(PKG, "libbpe_corpus.so")
 
 
@@ -17,10 +17,10 @@ class Stats(C.Structure):
         "n_input", "n_merges", "n_tokens", "ranks_applied", "same_bucket_ties", "threshold_edges", "resolver_runs",
         "census_runs", "table_rehashes", "table_capacity", "final_distinct", "kernel_launches", "replace_launches",
         "replace_bytes")] + [(n, C.c_double) for n in ("replace_ms", "ms_device", "ms_h2d", "ms_d2h", "ms_total")] + [
-        ("worker_buckets", C.c_uint64 * 16)]
+        ("worker_buckets", C.c_uint64 * 16)] + [(n, C.c_double) for n in ("select_ms", "apply_ms", "gap_ms")]
 
     def as_dict(self):
-        d = {n: getattr(self, n) for n, _ in self._fields_[:-1]}
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n != "worker_buckets"}
         d["worker_buckets"] = list(self.worker_buckets)
         return d
 

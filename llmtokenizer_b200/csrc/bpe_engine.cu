@@ -8,6 +8,7 @@
 // There is no CPU fallback anywhere in this file: without a CUDA device every entry point fails.
 #include "../../include/bpe_cuda.h"
 #include "bpe_kernels.cuh"
+#include "bpe_replace.cuh"
 #include "bpe_resolver.cuh"
 
 #include <cuda_runtime.h>
@@ -119,6 +120,10 @@ struct bpe_cuda_ctx
     // control block
     DevState *d_st = nullptr;
     DevState *h_st = nullptr; // pinned
+    // ranged layout: per buffer, length and edge tokens of every range
+    u32 *d_rcnt[2] = {nullptr, nullptr};
+    u32 *d_redge[2] = {nullptr, nullptr};
+    int rmax = 296;
     // tile descriptors
     u64 *d_desc = nullptr;
     u32 *d_pdesc = nullptr;
@@ -156,11 +161,14 @@ struct bpe_cuda_ctx
     // options
     int profile_replace = 0;
     int batch_steps = 64;
-    int smem_hist_max_vocab = 2048;
+    int smem_hist_max_vocab = 1792; // 28 KB of privatised delta counters: two CTAs of the streaming kernel still fit an SM
     int force_census = 0;
+    int use_stream = 1;
     int replace_occ[2] = {0, 0};
+    int stream_occ[2] = {0, 0}; // CTAs per SM of replace_stream_kernel<false>, <true> at the largest histogram
     // profiling events
     std::vector<cudaEvent_t> prof;
+    std::vector<unsigned char> prof_tag;
     size_t prof_used = 0;
     // results
     size_t res_n_merges = 0, res_n_tokens = 0;
@@ -186,7 +194,8 @@ static int ensure_bytes(bpe_cuda_ctx *c, size_t n)
 
 static int ensure_stream_buffers(bpe_cuda_ctx *c, size_t n)
 {
-    const size_t need = round_up(n, 16) + 64; // 4 slots in front, slack behind for whole-vector stores
+    // 4 slots in front; behind: the streaming kernel copies whole tiles (+ halo) and the halos are written in place
+    const size_t need = round_up(n, V_TILE) + V_TILE + 64;
     if (need > c->tok_cap)
     {
         for (int i = 0; i < 2; i++)
@@ -365,6 +374,13 @@ static int setup_kernels(bpe_cuda_ctx *c)
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, replace_kernel<false>, R_THREADS, replace_smem_bytes(false, 0)));
     c->replace_occ[0] = std::max(1, occ);
+    CU(cudaFuncSetAttribute(replace_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(replace_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, replace_stream_kernel<false>, V_THREADS, stream_smem_bytes(false, 0)));
+    c->stream_occ[0] = std::max(1, occ);
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, replace_stream_kernel<true>, V_THREADS,
+                                                     stream_smem_bytes(true, (u32)std::max(1, c->smem_hist_max_vocab) - 1)));
+    c->stream_occ[1] = std::max(1, occ);
     return 0;
 }
 
@@ -415,6 +431,22 @@ static int ensure_resolver(bpe_cuda_ctx *c, u64 n, u32 slices)
     return 0;
 }
 
+// profiling marks: the interval that ends at a mark is charged to the mark's class
+enum
+{
+    PT_GAP = 0,
+    PT_SELECT = 1,
+    PT_REPLACE = 2,
+    PT_APPLY = 3
+};
+static inline void prof_mark(bpe_cuda_ctx *c, int tag)
+{
+    if (!c->profile_replace || c->prof_used >= c->prof.size())
+        return;
+    c->prof_tag[c->prof_used] = (unsigned char)tag;
+    cudaEventRecord(c->prof[c->prof_used++], c->stream);
+}
+
 static int pos_grid(bpe_cuda_ctx *c, u64 n) { return (int)std::max<u64>(1, std::min<u64>((n + 255) / 256, (u64)c->sm_count * 8)); }
 
 // the 16-slice distinct-pair census that keeps the worker tables' bucket counts exact
@@ -430,8 +462,10 @@ static int enqueue_census(bpe_cuda_ctx *c, u64 n_upper, int resolver)
 }
 
 // enqueue one merge step; z is the id the step will create if it runs
-static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool with_select, bool census = false)
+static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool with_select, bool census = false,
+                        bool ranged = false)
 {
+    prof_mark(c, PT_GAP);
     if (with_select)
     {
         if (encode)
@@ -457,15 +491,21 @@ static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool w
     }
     const u64 tiles = std::max<u64>(1, (n_upper + R_TILE - 1) / R_TILE);
     const int grid = (int)std::min<u64>(tiles, (u64)c->sm_count * (u64)occ);
-    const bool prof = c->profile_replace && c->prof_used + 2 <= c->prof.size();
-    if (prof)
-        CU(cudaEventRecord(c->prof[c->prof_used++], c->stream));
-    if (hist)
+    prof_mark(c, PT_SELECT);
+    if (ranged)
+    {
+        // RANGED stream, a != b: one CTA per range, no dependency between CTAs (a == b pauses the loop instead)
+        const size_t vsmem = stream_smem_bytes(hist, z);
+        if (hist)
+            replace_stream_kernel<true><<<c->rmax, V_THREADS, vsmem, c->stream>>>(c->d_st, c->d_delta);
+        else
+            replace_stream_kernel<false><<<c->rmax, V_THREADS, vsmem, c->stream>>>(c->d_st, c->d_delta);
+    }
+    else if (hist)
         replace_kernel<true><<<grid, R_THREADS, smem, c->stream>>>(c->d_st, c->d_desc, c->d_pdesc, c->d_delta);
     else
         replace_kernel<false><<<grid, R_THREADS, smem, c->stream>>>(c->d_st, c->d_desc, c->d_pdesc, c->d_delta);
-    if (prof)
-        CU(cudaEventRecord(c->prof[c->prof_used++], c->stream));
+    prof_mark(c, PT_REPLACE);
     c->launches++;
     c->stats.replace_launches++;
     if (c->world > 1)
@@ -478,6 +518,7 @@ static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool w
     const int agrid = (int)std::min<u64>((4ull * (z + 1) + 255) / 256, (u64)c->sm_count * 4);
     apply_kernel<<<agrid, 256, 0, c->stream>>>(c->d_st, c->d_delta_red, c->d_delta);
     c->launches++;
+    prof_mark(c, PT_APPLY);
     return 0;
 }
 
@@ -543,9 +584,30 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
             if (census && (rc = ensure_resolver(c, h->n, stat ? REF_THREADS : 1)))
                 return rc;
         }
+        // The streaming kernel works on the RANGED layout; everything that needs positions in one dense
+        // array (static regime, census) keeps the stream dense and uses the general kernel.
+        const bool ranged = c->use_stream && !census && !h->static_mode && h->n_global >= STATIC_LIMIT && h->n > 0;
+        if (ranged && h->layout == LAYOUT_DENSE)
+        {
+            partition_kernel<<<1, RANGE_MAX, 0, c->stream>>>(c->d_st);
+            c->launches++;
+        }
+        else if (!ranged && h->layout == LAYOUT_RANGED)
+        {
+            repack_kernel<<<RANGE_MAX, 256, 0, c->stream>>>(c->d_st);
+            c->launches++;
+        }
         for (u64 g = 0; g < G; g++)
-            if ((rc = enqueue_step(c, (u32)(z0 + g), h->n, encode, true, census)))
+            if ((rc = enqueue_step(c, (u32)(z0 + g), h->n, encode, true, census, ranged)))
                 return rc;
+        CU(cudaGetLastError());
+        if ((rc = poll_state(c)))
+            return rc;
+    }
+    if (c->h_st->layout == LAYOUT_RANGED)
+    {
+        repack_kernel<<<RANGE_MAX, 256, 0, c->stream>>>(c->d_st);
+        c->launches++;
         CU(cudaGetLastError());
         if ((rc = poll_state(c)))
             return rc;
@@ -584,6 +646,15 @@ static int init_state(bpe_cuda_ctx *c, u64 n_local, u64 max_merges, bool encode,
     s.enc_merges = c->d_enc_merges;
     s.enc_total = enc_total;
     s.static_mode = 0;
+    s.use_stream = (u32)c->use_stream;
+    s.layout = s.layout_next = LAYOUT_DENSE;
+    s.rmax = (u32)c->rmax;
+    for (int i = 0; i < 2; i++)
+    {
+        s.rcnt[i] = c->d_rcnt[i];
+        s.redge[i] = c->d_redge[i];
+    }
+    s.pad_ctl = getenv("BPE_CUDA_FAKE_EXCL") ? (u32)atoi(getenv("BPE_CUDA_FAKE_EXCL")) : 0u;
     (void)encode;
     CU(cudaMemcpyAsync(c->d_st, &s, sizeof s, cudaMemcpyHostToDevice, c->stream));
     return 0;
@@ -608,6 +679,13 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
         return rc;
     if (!c->d_dense)
         CU(cudaMalloc(&c->d_dense, 65536 * sizeof(u32)));
+    for (int i = 0; i < 2; i++)
+        if (!c->d_rcnt[i])
+        {
+            CU(cudaMalloc(&c->d_rcnt[i], RANGE_MAX * sizeof(u32)));
+            CU(cudaMalloc(&c->d_redge[i], RANGE_MAX * EDGE_WORDS * sizeof(u32)));
+        }
+    c->rmax = std::min(RANGE_MAX, c->sm_count * c->stream_occ[0]);
     c->sel_grid = c->sm_count * 2;
     // fresh table
     table_free(c);
@@ -646,7 +724,8 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
     CU(cudaMemsetAsync(c->d_dense, 0, 65536 * sizeof(u32), c->stream));
     if (c->profile_replace && c->prof.empty())
     {
-        c->prof.resize(2 * 70000);
+        c->prof.resize(4 * 70000);
+        c->prof_tag.resize(c->prof.size());
         for (auto &e : c->prof)
             CU(cudaEventCreate(&e));
     }
@@ -748,14 +827,17 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
     }
     if (c->profile_replace)
     {
-        double tot = 0;
-        for (size_t i = 0; i + 1 < c->prof_used; i += 2)
+        double tot[4] = {0, 0, 0, 0};
+        for (size_t i = 0; i + 1 < c->prof_used; i++)
         {
             float e = 0;
             CU(cudaEventElapsedTime(&e, c->prof[i], c->prof[i + 1]));
-            tot += e;
+            tot[c->prof_tag[i + 1] & 3] += e;
         }
-        c->stats.replace_ms = tot;
+        c->stats.gap_ms = tot[PT_GAP];
+        c->stats.select_ms = tot[PT_SELECT];
+        c->stats.replace_ms = tot[PT_REPLACE];
+        c->stats.apply_ms = tot[PT_APPLY];
     }
     c->stats.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (stats_out)
@@ -781,6 +863,21 @@ static int resolve_pause(bpe_cuda_ctx *c, bool encode)
 {
     DevState *h = c->h_st;
     int rc;
+    if (h->layout == LAYOUT_RANGED)
+    {
+        // everything below works on positions of one dense array
+        repack_kernel<<<RANGE_MAX, 256, 0, c->stream>>>(c->d_st);
+        c->launches++;
+    }
+    if (h->pause & PAUSE_SAME)
+    {
+        // the merge (a == a) is already committed: run its pass with the general kernel
+        resume_kernel<<<1, 1, 0, c->stream>>>(c->d_st);
+        c->launches++;
+        if ((rc = ensure_delta(c, (size_t)(256 + h->merges_done + 2))))
+            return rc;
+        return enqueue_step(c, (u32)(256 + h->merges_done - 1), h->n, encode, false);
+    }
     if (h->pause & PAUSE_STATIC)
     {
         // the select kernel latched static_mode; nothing else to do but resume
@@ -880,7 +977,16 @@ int bpe_cuda_ctx_create(int device, bpe_cuda_ctx_t **out)
     if (const char *e = getenv("BPE_CUDA_BATCH_STEPS"))
         c->batch_steps = std::max(1, atoi(e));
     if (const char *e = getenv("BPE_CUDA_SMEM_HIST_MAX_VOCAB"))
+    {
         c->smem_hist_max_vocab = atoi(e);
+        if ((rc = setup_kernels(c)))
+        {
+            delete c;
+            return rc;
+        }
+    }
+    if (const char *e = getenv("BPE_CUDA_USE_STREAM"))
+        c->use_stream = atoi(e) != 0;
     *out = c;
     return 0;
 }
@@ -903,6 +1009,11 @@ void bpe_cuda_ctx_destroy(bpe_cuda_ctx_t *c)
     cudaFreeHost(c->h_st);
     cudaFree(c->d_desc);
     cudaFree(c->d_pdesc);
+    for (int i = 0; i < 2; i++)
+    {
+        cudaFree(c->d_rcnt[i]);
+        cudaFree(c->d_redge[i]);
+    }
     cudaFree(c->d_delta);
     if (c->d_delta_red != c->d_delta)
         cudaFree(c->d_delta_red);
@@ -1058,9 +1169,14 @@ int bpe_cuda_ctx_set_option(bpe_cuda_ctx_t *c, const char *name, long long value
     else if (!strcmp(name, "batch_steps"))
         c->batch_steps = (int)std::max<long long>(1, value);
     else if (!strcmp(name, "smem_hist_max_vocab"))
-        c->smem_hist_max_vocab = (int)value;
+    {
+        c->smem_hist_max_vocab = (int)std::min<long long>(value, 8192);
+        return setup_kernels(c);
+    }
     else if (!strcmp(name, "force_census"))
         c->force_census = (int)value;
+    else if (!strcmp(name, "use_stream"))
+        c->use_stream = (int)(value != 0);
     else
         return BPE_CUDA_ERR_ARG;
     return 0;

@@ -39,10 +39,18 @@ enum : u32
 };
 enum : u32
 {
-    PAUSE_TIE = 1,   // >= 2 maximal pairs share the winning bucket: chain order decides
-    PAUSE_EDGE = 2,  // D sits exactly on a doubling threshold of the merged table
-    PAUSE_STATIC = 4 // stream fell below 1,048,576 tokens: reference switches to static slicing
+    PAUSE_TIE = 1,    // >= 2 maximal pairs share the winning bucket: chain order decides
+    PAUSE_EDGE = 2,   // D sits exactly on a doubling threshold of the merged table
+    PAUSE_STATIC = 4, // stream fell below 1,048,576 tokens: reference switches to static slicing
+    PAUSE_SAME = 8    // a == b was selected (and committed) while the stream is RANGED: needs the general kernel
 };
+enum : u32
+{
+    LAYOUT_DENSE = 0,
+    LAYOUT_RANGED = 1
+};
+constexpr int RANGE_MAX = 320;  // ranges per shard (= CTAs of the streaming kernel)
+constexpr int EDGE_WORDS = 8;   // per range: [0..2] first three tokens, [3] second to last, [4] last (SENT where absent)
 enum : u32
 {
     ERR_TABLE_FULL = 1,
@@ -68,7 +76,17 @@ struct DevState
     u32 skip; // encode: this rank's pair does not occur anywhere -> no pass
     // loop control
     u32 stop, pause, err, static_mode;
+    u32 use_stream, pad_ctl; // a != b passes run in replace_stream_kernel (bpe_replace.cuh)
     u64 merges_done, max_merges;
+    // Stream layout.  DENSE: tok[cur][0..n).  RANGED: the shard is cut into nr ranges that are compacted
+    // independently (one CTA each, no prefix scan across CTAs): range c lives at tok[buf][c*rcap ..
+    // c*rcap + rcnt[buf][c]); redge[buf][8c..] holds its first three and last two tokens.
+    u32 layout, layout_next;
+    u32 nr, rmax;
+    u64 rcap;
+    u32 *rcnt[2];
+    u32 *redge[2];
+    u32 rp_done, pad_rp;
     // pair table: open addressing, key = a | b<<32, meta = murmur3 | count<<32
     u64 *tkey;
     u64 *tmeta;
@@ -243,6 +261,44 @@ __device__ __forceinline__ u64 table_insert(DevState *st, u64 key, u32 h)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Stream views that work for both layouts (ends of the shard only; the bulk is never touched here).
+struct StreamEnds
+{
+    u32 first[3]; // first three tokens (SENT where the shard is shorter)
+    u32 last2[2]; // second to last, last
+};
+__device__ inline void stream_ends(const DevState *st, u32 buf, u32 layout, u64 n, StreamEnds &e)
+{
+    for (int k = 0; k < 3; k++)
+        e.first[k] = SENT;
+    e.last2[0] = e.last2[1] = SENT;
+    const u32 *t = st->tok[buf];
+    if (layout == LAYOUT_DENSE)
+    {
+        for (u64 k = 0; k < 3 && k < n; k++)
+            e.first[k] = t[k];
+        if (n >= 1)
+            e.last2[1] = t[n - 1];
+        if (n >= 2)
+            e.last2[0] = t[n - 2];
+        return;
+    }
+    const u32 *cnt = st->rcnt[buf], *ed = st->redge[buf];
+    int got = 0;
+    for (u32 q = 0; q < st->nr && got < 3; q++)
+        for (u32 k = 0; k < 3 && k < cnt[q] && got < 3; k++)
+            e.first[got++] = ed[q * EDGE_WORDS + k];
+    got = 0;
+    for (int q = (int)st->nr - 1; q >= 0 && got < 2; q--)
+    {
+        if (cnt[q] >= 1 && got < 2)
+            e.last2[1 - got++] = ed[q * EDGE_WORDS + 4];
+        if (cnt[q] >= 2 && got < 2)
+            e.last2[1 - got++] = ed[q * EDGE_WORDS + 3];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K0 + K1: widen bytes to u32 tokens (bpe.c:580-584) and histogram all adjacent byte pairs into
 // a dense 256x256 table (every overlapping occurrence counts, bpe.c:460-471).  While all ids are
 // < 256 the dense table replaces the hash table.  16 bytes per thread: one 128-bit load, four
@@ -374,29 +430,40 @@ __global__ void edge_record_kernel(DevState *st, int32_t *delta_local, int use_n
 {
     if (st->stop != STOP_RUN && use_next)
         return;
-    const u32 *s = use_next ? st->tok[st->cur ^ 1] : st->tok[st->cur];
-    const u64 len = (use_next && !st->skip) ? st->n_next : st->n;
-    if (use_next && st->skip)
-        s = st->tok[st->cur];
+    const bool nxt = use_next && !st->skip;
+    const u32 buf = nxt ? (st->cur ^ 1u) : st->cur;
+    const u32 layout = nxt ? st->layout_next : st->layout;
+    const u64 len = nxt ? st->n_next : st->n;
+    const u32 *s = st->tok[buf];
     const int lane = threadIdx.x;
     u32 *rec = reinterpret_cast<u32 *>(delta_local) + st->rank * REC_INTS;
-    // trailing run of the last token, 32 tokens per step
+    StreamEnds e;
+    stream_ends(st, buf, layout, len, e);
+    // trailing run of the last token, 32 tokens per step, range by range from the back
     u64 run = 0;
     bool uniform = false;
     if (len)
     {
-        const u32 last = s[len - 1];
-        u64 pos = len; // tokens [pos, len) are known to equal `last`
-        for (;;)
+        const u32 last = e.last2[1];
+        const int nseg = (layout == LAYOUT_DENSE) ? 1 : (int)st->nr;
+        bool open = true; // the run may still extend further to the left
+        for (int q = nseg - 1; q >= 0 && open; q--)
         {
-            const i64 i = (i64)pos - 1 - lane;
-            const bool eq = (i >= 0) && (s[i] == last);
-            const u32 m = __ballot_sync(0xFFFFFFFFu, eq);
-            const int c = (m == 0xFFFFFFFFu) ? 32 : (__ffs(~m) - 1);
-            run += (u64)c;
-            pos -= (u64)c;
-            if (c < 32 || pos == 0)
-                break;
+            const u32 *p = (layout == LAYOUT_DENSE) ? s : s + (u64)q * st->rcap;
+            const u64 cnt = (layout == LAYOUT_DENSE) ? len : (u64)st->rcnt[buf][q];
+            u64 pos = cnt; // tokens [pos, cnt) of this piece are known to equal `last`
+            while (pos > 0)
+            {
+                const i64 i = (i64)pos - 1 - lane;
+                const bool eq = (i >= 0) && (p[i] == last);
+                const u32 m = __ballot_sync(0xFFFFFFFFu, eq);
+                const int c = (m == 0xFFFFFFFFu) ? 32 : (__ffs(~m) - 1);
+                run += (u64)c;
+                pos -= (u64)c;
+                if (c < 32)
+                    break;
+            }
+            open = (pos == 0); // the whole piece is part of the run: it may continue in the piece in front
         }
         uniform = (run == len);
     }
@@ -405,9 +472,9 @@ __global__ void edge_record_kernel(DevState *st, int32_t *delta_local, int use_n
         rec[0] = (u32)len;
         rec[1] = (u32)(len >> 32);
         for (int k = 0; k < 3; k++)
-            rec[2 + k] = ((u64)k < len) ? s[k] : SENT;
-        rec[6] = len >= 1 ? s[len - 1] : SENT;
-        rec[5] = len >= 2 ? s[len - 2] : SENT;
+            rec[2 + k] = e.first[k];
+        rec[5] = e.last2[0];
+        rec[6] = e.last2[1];
         rec[7] = (u32)(run & 1ull) | ((u32)uniform << 1);
     }
 }
@@ -572,8 +639,10 @@ __device__ inline void dynamic_regime_census(DevState *st, const u32 *rec_all)
     }
     else if (st->n >= 2)
     {
-        x = st->tok[st->cur][st->n - 2];
-        y = st->tok[st->cur][st->n - 1];
+        StreamEnds e;
+        stream_ends(st, st->cur, st->layout, st->n, e);
+        x = e.last2[0];
+        y = e.last2[1];
     }
     if (x == SENT || y == SENT)
         return;
@@ -599,6 +668,7 @@ __device__ inline void commit_merge(DevState *st, u32 a, u32 b, u32 freq, const 
         st->n_global = st->n;
     if (!encode && st->n_global >= STATIC_LIMIT)
         dynamic_regime_census(st, rec_all);
+    st->n_next = 0; // the ranged streaming kernel accumulates its ranges' new lengths here
     st->n_hist[k] = st->n_global;
     st->merges_done = k + 1;
     st->epoch = st->epoch + 1;
@@ -724,6 +794,12 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(DevState *st, const
     }
     const u64 key = st->tkey[s];
     commit_merge(st, (u32)(key & 0xFFFFFFFFull), (u32)(key >> 32), freq, rec_all);
+    if (st->a == st->b && st->layout == LAYOUT_RANGED)
+    {
+        // run-parity pairing needs the general kernel on a dense stream: the host repacks, then resumes
+        st->pause = PAUSE_SAME;
+        st->stop = STOP_PAUSE;
+    }
 }
 
 // encode: the "selection" is simply the next rank of the given merge list; a rank whose pair does
@@ -746,7 +822,14 @@ __global__ void select_rank_kernel(DevState *st, const int32_t *delta_reduced)
     if (cnt == 0)
         st->skip = 1;
     else
+    {
         st->ranks_applied++;
+        if (a == b && st->layout == LAYOUT_RANGED)
+        {
+            st->pause = PAUSE_SAME;
+            st->stop = STOP_PAUSE;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -800,6 +883,8 @@ __global__ void __launch_bounds__(R_THREADS) replace_kernel(DevState *st, u64 *d
 {
     if (st->stop != STOP_RUN || st->skip)
         return;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        st->layout_next = LAYOUT_DENSE;
     extern __shared__ __align__(16) u32 smem[];
     u32 *s_tok = smem;                                             // R_TILE + 8 tokens
     int32_t *s_hist = reinterpret_cast<int32_t *>(smem + R_TILE + 8); // 4*(z+1) counters when SMEM_HIST
@@ -1201,6 +1286,7 @@ __global__ void __launch_bounds__(256) apply_kernel(DevState *st, int32_t *delta
         }
         st->n = st->n_next;
         st->cur ^= 1u;
+        st->layout = st->layout_next;
     }
 }
 

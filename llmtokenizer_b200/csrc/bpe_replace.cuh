@@ -1,0 +1,611 @@
+// K3 for a != b (the overwhelmingly common case): fused replace + prefix-scan compaction + pair-count
+// deltas as a TMA-fed, warp-specialised streaming kernel (sm_100a).
+//
+// Reference loop being replaced: bpe/src/bpe.c:760-772 (greedy left-to-right rewrite) plus the
+// recount of the next iteration (bpe.c:460-471), which the delta vectors make unnecessary.
+//
+// One streaming pass, 4*n_k bytes in, 4*n_{k+1} bytes out.
+//
+// Layout.  Measured on B200 (profiles/): a single-pass scan whose tiles are chained
+// through global memory (decoupled look-back, a central scan warp, or row-wise aggregates - all three
+// were built and timed) tops out at 2.1-3.3 TB/s on this path, because every store waits for the
+// slowest of the ~1,000 tile loads in flight in front of it, while the same kernel with no
+// dependency between CTAs streams at 5.7 TB/s.  So the shard is kept RANGED: cut into nr <= 320
+// ranges of whole tiles, one CTA per range, each range compacted in place of itself (range c lives at
+// tok[buf][c*rcap .. c*rcap + rcnt[buf][c])).  The prefix scan is then local to the CTA - a running
+// sum - and CTAs never wait for one another.  What crosses a range boundary is the same
+// pair-independent edge information the GPUs exchange at shard boundaries (first three / last two
+// tokens of each range, published by the CTA that wrote them), read at the start of the next pass.
+// repack_kernel turns the stream back into one dense array when something needs that (a == b merges,
+// the exact tie-break kernels, the static regime below 1,048,576 tokens, the final download).
+//
+// Inside a CTA (10 warps) a ring of shared-memory stages holds one 4,096-token tile (32 "iterations"
+// of 128 tokens) each:
+//   producer (1 warp)   one 1-D bulk copy (TMA: cp.async.bulk + mbarrier complete_tx) per tile;
+//   scanners (4 warps)  8 iterations each: a lane owns one 128-bit chunk (conflict-free LDS.128),
+//                       finds the replacements that start on it, counts kept tokens per iteration
+//                       (ballots), emits the pair-count deltas;
+//   offsets (1 warp)    turns the 32 per-iteration counts into output offsets (running sum), resolves
+//                       the range's halos at the start and publishes its edges at the end;
+//   storers (4 warps)   re-read the tile from shared memory and write the kept tokens: an iteration
+//                       without replacements (the common case once the pair is rarer than ~1 in 1,000
+//                       tokens) goes registers -> global with 128-bit stores realigned by warp
+//                       shuffles; the others compact through a 136-word per-warp staging buffer.
+#pragma once
+#include "bpe_kernels.cuh"
+
+namespace bpe
+{
+
+constexpr int V_SCAN_WARPS = 4;
+constexpr int V_STORE_WARPS = 4;
+constexpr int V_ITERS = 32;                        // iterations (128 tokens) per tile
+constexpr int V_TILE = V_ITERS * 128;              // 4,096 tokens = 16 KB
+constexpr int V_THREADS = (V_SCAN_WARPS + V_STORE_WARPS + 2) * 32;
+#ifndef BPE_V_STAGES
+#define BPE_V_STAGES 5
+#endif
+constexpr int V_STAGES = BPE_V_STAGES;
+constexpr int V_STAGE_WORDS = V_TILE + 8;          // 4 tokens of halo on either side
+constexpr int V_STAGING_WORDS = 136;               // per storer warp: 128 tokens + alignment phase
+constexpr u32 V_TILE_BYTES = V_STAGE_WORDS * 4;
+constexpr int V_WARP_PRODUCER = V_SCAN_WARPS + V_STORE_WARPS;
+constexpr int V_WARP_OFFSETS = V_WARP_PRODUCER + 1;
+
+__host__ __device__ inline size_t stream_smem_bytes(bool hist, u32 z)
+{
+    return (size_t)V_STAGES * V_TILE_BYTES + (size_t)V_STORE_WARPS * V_STAGING_WORDS * 4 + (hist ? 16 * ((size_t)z + 1) : 0);
+}
+
+// ---- mbarrier / bulk-copy wrappers (PTX ISA: mbarrier, cp.async.bulk) --------------------------
+__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u64 *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64 *bar, u32 bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(u64 *bar, u32 parity)
+{
+    u32 ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_addr(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
+{
+    const u32 addr = smem_addr(bar);
+    u32 ok;
+    do
+    {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(addr), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, u32 bytes, u64 *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void scanner_bar()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(V_SCAN_WARPS * 32) : "memory");
+}
+__device__ __forceinline__ void st_v4(u32 *p, u32 x, u32 y, u32 z, u32 w)
+{
+    *reinterpret_cast<uint4 *>(p) = make_uint4(x, y, z, w);
+}
+__device__ __forceinline__ void st_v2(u32 *p, u32 x, u32 y) { *reinterpret_cast<uint2 *>(p) = make_uint2(x, y); }
+
+
+// per-stage bookkeeping in shared memory
+struct StageMeta
+{
+    u32 excl;            // output offset of the tile inside the range (running sum)
+    u32 slowmask;        // bit j: iteration j has replacements / removals / invalid tokens
+    u32 cnt[V_ITERS];    // kept tokens per iteration
+    u32 pre[V_ITERS];    // exclusive prefix of cnt
+};
+
+// Replacements that start on my chunk and whether my first token is removed, for iteration j of the
+// tile staged at sin (sin[p] = token at tile position p, p in [-4, V_TILE + 4)).
+//   bits 0..3: a replacement starts on token k; bit 4: token 0 is the `b` of one that starts in front
+// Returns false (and bits = 0) when the whole warp has nothing to do in this iteration.
+__device__ __forceinline__ bool iter_bits(const u32 *sin, int j, int lane, u32 a, u32 b, u32 valid, bool full, const uint4 &c,
+                                          u32 &bits, u32 &v)
+{
+    const u32 nxl = sin[(j + 1) * 128];
+    const u32 pvl = sin[j * 128 - 1];
+    u32 nx = __shfl_down_sync(0xFFFFFFFFu, c.x, 1);
+    if (lane == 31)
+        nx = nxl;
+    const u32 x0 = __shfl_sync(0xFFFFFFFFu, c.x, 0);
+    const u32 carry = (pvl == a && x0 == b) ? 1u : 0u;
+    bool m0 = (c.x == a) && (c.y == b);
+    bool m1 = (c.y == a) && (c.z == b);
+    bool m2 = (c.z == a) && (c.w == b);
+    bool m3 = (c.w == a) && (nx == b);
+    v = 4;
+    if (!full)
+    {
+        const u32 p = (u32)j * 128u + (u32)lane * 4u;
+        v = (p >= valid) ? 0u : ((valid - p < 4u) ? (valid - p) : 4u);
+        m0 = m0 && v > 0;
+        m1 = m1 && v > 1;
+        m2 = m2 && v > 2;
+        m3 = m3 && v > 3;
+    }
+    bits = 0;
+    if (!(__any_sync(0xFFFFFFFFu, m0 | m1 | m2 | m3) || carry || !full))
+        return false;
+    const u32 mb3 = __ballot_sync(0xFFFFFFFFu, m3);
+    const u32 r0 = (((mb3 << 1) | carry) >> lane) & 1u;
+    bits = (u32)m0 | ((u32)m1 << 1) | ((u32)m2 << 2) | ((u32)m3 << 3) | (r0 << 4);
+    return true;
+}
+__device__ __forceinline__ u32 keep_mask(u32 bits, u32 v) { return ((1u << v) - 1u) & ~((bits >> 4) | ((bits & 7u) << 1)) & 0xFu; }
+
+template <bool SMEM_HIST>
+__global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *st, int32_t *delta)
+{
+    if (st->stop != STOP_RUN || st->skip)
+        return;
+    const u32 a = st->a, b = st->b, z = st->z;
+    const u32 cta = blockIdx.x, nr = st->nr;
+    if (cta >= nr)
+        return;
+    const u32 ibuf = st->cur, obuf = st->cur ^ 1u;
+    const u64 rcap = st->rcap;
+    const u32 n = st->rcnt[ibuf][cta]; // tokens of my range
+    if (cta == 0 && threadIdx.x == 0)
+        st->layout_next = LAYOUT_RANGED;
+
+    extern __shared__ __align__(16) u32 smem[];
+    u32 *s_in = smem;                                       // V_STAGES x V_STAGE_WORDS
+    u32 *s_staging = smem + V_STAGES * V_STAGE_WORDS;       // V_STORE_WARPS x V_STAGING_WORDS
+    int32_t *s_hist = reinterpret_cast<int32_t *>(s_staging + V_STORE_WARPS * V_STAGING_WORDS);
+    __shared__ __align__(8) u64 s_full[V_STAGES], s_scanned[V_STAGES], s_ready[V_STAGES], s_empty[V_STAGES], s_halo_ready;
+    __shared__ StageMeta s_meta[V_STAGES];
+    __shared__ u32 s_halo[5]; // tokens at range positions -2, -1, n, n+1, n+2
+
+    const u32 *__restrict__ in = st->tok[ibuf] + (u64)cta * rcap;
+    u32 *__restrict__ out = st->tok[obuf] + (u64)cta * rcap;
+    const u32 ntiles = (n + V_TILE - 1) / V_TILE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int32_t *gdelta = delta + HDR_INTS;
+
+    if (tid == 0)
+    {
+        for (int s = 0; s < V_STAGES; s++)
+        {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_scanned[s], V_SCAN_WARPS);
+            mbar_init(&s_ready[s], 1);
+            mbar_init(&s_empty[s], V_STORE_WARPS);
+            s_meta[s].slowmask = 0;
+        }
+        mbar_init(&s_halo_ready, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (SMEM_HIST)
+        for (u32 i = tid; i < 4 * (z + 1); i += V_THREADS)
+            s_hist[i] = 0;
+    __syncthreads();
+
+    if (warp == V_WARP_PRODUCER)
+    {
+        // ---------------- producer ----------------
+        if (lane == 0)
+        {
+            for (u32 t = 0; t < ntiles; t++)
+            {
+                const u32 s = t % V_STAGES;
+                if (t >= V_STAGES)
+                    mbar_wait(&s_empty[s], ((t / V_STAGES) & 1u) ^ 1u);
+                s_meta[s].slowmask = 0; // every storer is done with the previous tile of this stage
+                mbar_arrive_expect_tx(&s_full[s], V_TILE_BYTES);
+                bulk_load(s_in + s * V_STAGE_WORDS, in + (u64)t * V_TILE - 4, V_TILE_BYTES, &s_full[s]);
+            }
+        }
+    }
+    else if (warp == V_WARP_OFFSETS)
+    {
+        // ---------------- halos, output offsets (the range-local prefix scan), new edges ----------------
+        if (lane == 0)
+        {
+            // the two tokens in front of my range and the three behind it, skipping empty ranges; beyond
+            // the shard: the neighbouring GPUs' tokens (SENT at the true ends of the corpus)
+            const u32 *cnt = st->rcnt[ibuf], *ed = st->redge[ibuf];
+            u32 near[2];
+            int got = 0;
+            for (int q = (int)cta - 1; q >= 0 && got < 2; q--)
+            {
+                if (cnt[q] >= 1 && got < 2)
+                    near[got++] = ed[q * EDGE_WORDS + 4];
+                if (cnt[q] >= 2 && got < 2)
+                    near[got++] = ed[q * EDGE_WORDS + 3];
+            }
+            s_halo[1] = got >= 1 ? near[0] : st->halo_before[1];
+            s_halo[0] = got >= 2 ? near[1] : (got == 1 ? st->halo_before[1] : st->halo_before[0]);
+            got = 0;
+            for (u32 q = cta + 1; q < nr && got < 3; q++)
+                for (u32 k = 0; k < 3 && k < cnt[q] && got < 3; k++)
+                    s_halo[2 + got++] = ed[q * EDGE_WORDS + k];
+            for (int k = 0; got < 3; k++)
+                s_halo[2 + got++] = st->halo_after[k];
+            mbar_arrive(&s_halo_ready);
+        }
+        __syncwarp();
+        u32 run = 0; // kept tokens of the tiles in front, i.e. the output offset inside the range
+        for (u32 t = 0; t < ntiles; t++)
+        {
+            const u32 s = t % V_STAGES;
+            StageMeta &sm = s_meta[s];
+            mbar_wait(&s_scanned[s], (t / V_STAGES) & 1u);
+            const u32 cnt = sm.cnt[lane];
+            u32 incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const u32 v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o)
+                    incl += v;
+            }
+            sm.pre[lane] = incl - cnt;
+            __syncwarp();
+            if (lane == 0)
+            {
+                sm.excl = run;
+                mbar_arrive(&s_ready[s]);
+            }
+            run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+        // wait for the storers of the last tiles, then publish the range's new length and edges
+        for (u32 t = (ntiles > (u32)V_STAGES ? ntiles - V_STAGES : 0); t < ntiles; t++)
+            mbar_wait(&s_empty[t % V_STAGES], (t / V_STAGES) & 1u);
+        __threadfence_block();
+        if (lane == 0)
+        {
+            u32 *oe = st->redge[obuf] + cta * EDGE_WORDS;
+            const volatile u32 *o = out;
+            for (u32 k = 0; k < 3; k++)
+                oe[k] = (k < run) ? o[k] : SENT;
+            oe[3] = run >= 2 ? o[run - 2] : SENT;
+            oe[4] = run >= 1 ? o[run - 1] : SENT;
+            st->rcnt[obuf][cta] = run;
+            atomicAdd(&st->n_next, (u64)run);
+        }
+    }
+    else if (warp < V_SCAN_WARPS)
+    {
+        // ---------------- scanners ----------------
+        constexpr int PER = V_ITERS / V_SCAN_WARPS;
+        for (u32 t = 0; t < ntiles; t++)
+        {
+            const u32 s = t % V_STAGES;
+            StageMeta &sm = s_meta[s];
+            mbar_wait(&s_full[s], (t / V_STAGES) & 1u);
+            const u32 base = t * V_TILE;
+            const u32 valid = (n - base < (u32)V_TILE) ? (n - base) : (u32)V_TILE;
+            const bool full = (valid == (u32)V_TILE);
+            u32 *sin = s_in + s * V_STAGE_WORDS + 4;
+            if (t == 0 || t == ntiles - 1)
+            {
+                // first / last tile of the range: its halo comes from the neighbouring ranges
+                if (warp == 0)
+                {
+                    mbar_wait(&s_halo_ready, 0);
+                    if (lane == 0)
+                    {
+                        if (t == 0)
+                        {
+                            sin[-2] = s_halo[0];
+                            sin[-1] = s_halo[1];
+                        }
+                        if (t == ntiles - 1)
+                        {
+                            sin[valid] = s_halo[2];
+                            sin[valid + 1] = s_halo[3];
+                            sin[valid + 2] = s_halo[4];
+                        }
+                    }
+                }
+                scanner_bar();
+            }
+            u32 slow = 0;
+#pragma unroll 2
+            for (int jj = 0; jj < PER; jj++)
+            {
+                const int j = warp * PER + jj;
+                const uint4 c = *reinterpret_cast<const uint4 *>(sin + j * 128 + lane * 4);
+                u32 bits, v, ktj = 128;
+                if (iter_bits(sin, j, lane, a, b, valid, full, c, bits, v))
+                {
+                    slow |= 1u << j;
+                    ktj = __reduce_add_sync(0xFFFFFFFFu, (u32)__popc(keep_mask(bits, v)));
+                    // ---- pair-count deltas of the replacements that start on my tokens
+                    if (bits & 0xFu)
+                    {
+                        const int p0 = j * 128 + lane * 4;
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if ((bits >> k) & 1u)
+                            {
+                                const int p = p0 + k;
+                                const u32 xl = sin[p - 1], yr = sin[p + 2];
+                                const bool pm = (sin[p - 2] == a) && (xl == b); // a replacement ends right in front
+                                const bool nm = (yr == a) && (sin[p + 3] == b); // another one starts right behind
+                                if (xl != SENT)
+                                {
+                                    const u32 xn = pm ? z : xl;
+                                    if (SMEM_HIST)
+                                    {
+                                        atomicAdd(&s_hist[xl * 4 + 0], 1);
+                                        atomicAdd(&s_hist[xn * 4 + 2], 1);
+                                    }
+                                    else
+                                    {
+                                        atomicAdd(&gdelta[(u64)xl * 4 + 0], 1);
+                                        atomicAdd(&gdelta[(u64)xn * 4 + 2], 1);
+                                    }
+                                }
+                                if (yr != SENT && !nm)
+                                {
+                                    if (SMEM_HIST)
+                                    {
+                                        atomicAdd(&s_hist[yr * 4 + 1], 1);
+                                        atomicAdd(&s_hist[yr * 4 + 3], 1);
+                                    }
+                                    else
+                                    {
+                                        atomicAdd(&gdelta[(u64)yr * 4 + 1], 1);
+                                        atomicAdd(&gdelta[(u64)yr * 4 + 3], 1);
+                                    }
+                                }
+                            }
+                    }
+                }
+                if (lane == 0)
+                    sm.cnt[j] = ktj;
+            }
+            if (lane == 0)
+            {
+                if (slow)
+                    atomicOr(&sm.slowmask, slow);
+                mbar_arrive(&s_scanned[s]);
+            }
+            __syncwarp();
+        }
+    }
+    else
+    {
+        // ---------------- storers ----------------
+        const int sw = warp - V_SCAN_WARPS;
+        u32 *stg = s_staging + sw * V_STAGING_WORDS;
+        for (u32 t = 0; t < ntiles; t++)
+        {
+            const u32 s = t % V_STAGES;
+            StageMeta &sm = s_meta[s];
+            mbar_wait(&s_ready[s], (t / V_STAGES) & 1u);
+            const u32 base = t * V_TILE;
+            const u32 valid = (n - base < (u32)V_TILE) ? (n - base) : (u32)V_TILE;
+            const bool full = (valid == (u32)V_TILE);
+            const u32 *sin = s_in + s * V_STAGE_WORDS + 4;
+            const u32 excl = sm.excl;
+            const u32 slowmask = sm.slowmask;
+#pragma unroll 2
+            for (int j = sw; j < V_ITERS; j += V_STORE_WARPS)
+            {
+                const uint4 c = *reinterpret_cast<const uint4 *>(sin + j * 128 + lane * 4);
+                const u32 g = excl + sm.pre[j];
+                if (!((slowmask >> j) & 1u))
+                {
+                    // 128 kept tokens, contiguous in the output: 128-bit stores realigned by shuffles
+                    u32 *o = out + g + 4 * lane;
+                    const u32 ph = g & 3u;
+                    if (ph == 0)
+                        st_v4(o, c.x, c.y, c.z, c.w);
+                    else if (ph == 1)
+                    {
+                        const u32 t0 = __shfl_down_sync(0xFFFFFFFFu, c.x, 1), t1 = __shfl_down_sync(0xFFFFFFFFu, c.y, 1),
+                                  t2 = __shfl_down_sync(0xFFFFFFFFu, c.z, 1);
+                        if (lane < 31)
+                            st_v4(o + 3, c.w, t0, t1, t2);
+                        else
+                            o[3] = c.w;
+                        if (lane == 0)
+                        {
+                            o[0] = c.x;
+                            o[1] = c.y;
+                            o[2] = c.z;
+                        }
+                    }
+                    else if (ph == 2)
+                    {
+                        const u32 t0 = __shfl_down_sync(0xFFFFFFFFu, c.x, 1), t1 = __shfl_down_sync(0xFFFFFFFFu, c.y, 1);
+                        if (lane < 31)
+                            st_v4(o + 2, c.z, c.w, t0, t1);
+                        else
+                            st_v2(o + 2, c.z, c.w);
+                        if (lane == 0)
+                            st_v2(o, c.x, c.y);
+                    }
+                    else
+                    {
+                        const u32 t0 = __shfl_down_sync(0xFFFFFFFFu, c.x, 1);
+                        if (lane < 31)
+                            st_v4(o + 1, c.y, c.z, c.w, t0);
+                        else
+                        {
+                            o[1] = c.y;
+                            o[2] = c.z;
+                            o[3] = c.w;
+                        }
+                        if (lane == 0)
+                            o[0] = c.x;
+                    }
+                }
+                else
+                {
+                    // compaction through the per-warp staging buffer
+                    u32 bits, v;
+                    iter_bits(sin, j, lane, a, b, valid, full, c, bits, v);
+                    const u32 keep = keep_mask(bits, v);
+                    const u32 kc = (u32)__popc(keep);
+                    u32 incl = kc;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1)
+                    {
+                        const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                        if (lane >= o)
+                            incl += t;
+                    }
+                    const u32 ktj = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    const u32 ph = g & 3u;
+                    u32 rk = ph + incl - kc;
+                    const u32 tk[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if ((keep >> k) & 1u)
+                            stg[rk++] = ((bits >> k) & 1u) ? z : tk[k];
+                    __syncwarp();
+                    // stg[ph + i] <-> out[g + i], i in [0, ktj): aligned 16 B chunks line up on both sides
+                    u32 *ob = out + (g - ph); // 16 B aligned
+                    const u32 lo = ph, hi = ph + ktj;
+                    for (u32 q = lane; q * 4 < hi; q += 32)
+                    {
+                        const u32 w0 = q * 4;
+                        if (w0 >= lo && w0 + 4 <= hi)
+                            *reinterpret_cast<uint4 *>(ob + w0) = *reinterpret_cast<const uint4 *>(stg + w0);
+                        else
+                        {
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                if (w0 + k >= lo && w0 + k < hi)
+                                    ob[w0 + k] = stg[w0 + k];
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(&s_empty[s]);
+        }
+    }
+
+    if (SMEM_HIST)
+    {
+        __syncthreads();
+        for (u32 i = tid; i < 4 * (z + 1); i += V_THREADS)
+        {
+            const int32_t v = s_hist[i];
+            if (v)
+                atomicAdd(&gdelta[i], v);
+        }
+    }
+}
+
+
+
+// ---------------------------------------------------------------------------------------------
+// DENSE -> RANGED: cut tok[cur][0..n) into ranges of whole tiles, in place (a dense stream is a ranged
+// stream whose ranges are full).  One block.
+__global__ void __launch_bounds__(RANGE_MAX) partition_kernel(DevState *st)
+{
+    if (st->stop != STOP_RUN || st->layout != LAYOUT_DENSE)
+        return;
+    const u64 n = st->n;
+    const u64 tiles = (n + V_TILE - 1) / V_TILE;
+    u64 want = st->rmax ? st->rmax : 1;
+    if (want > tiles)
+        want = tiles;
+    const u64 per = want ? (tiles + want - 1) / want : 0; // tiles per range
+    const u64 rcap = per * V_TILE;
+    const u32 nr = per ? (u32)((tiles + per - 1) / per) : 0;
+    const u32 c = threadIdx.x;
+    if (c < nr)
+    {
+        const u32 *t = st->tok[st->cur] + (u64)c * rcap;
+        const u64 left = n - (u64)c * rcap;
+        const u32 cnt = (u32)(left < rcap ? left : rcap);
+        st->rcnt[st->cur][c] = cnt;
+        u32 *e = st->redge[st->cur] + c * EDGE_WORDS;
+        for (u32 k = 0; k < 3; k++)
+            e[k] = (k < cnt) ? t[k] : SENT;
+        e[3] = cnt >= 2 ? t[cnt - 2] : SENT;
+        e[4] = cnt >= 1 ? t[cnt - 1] : SENT;
+    }
+    __syncthreads();
+    if (c == 0)
+    {
+        st->nr = nr;
+        st->rcap = rcap;
+        st->layout = LAYOUT_RANGED;
+    }
+}
+
+// RANGED -> DENSE: range c is copied to its place in the dense stream of the other buffer (its offset
+// is the sum of the lower ranges' lengths: <= 320 numbers, summed by every CTA for itself).  The last
+// CTA to finish flips the buffers.  Runs whatever the loop state is (the host asks for it on pauses
+// and before the final download).
+__global__ void __launch_bounds__(256) repack_kernel(DevState *st)
+{
+    if (st->layout != LAYOUT_RANGED)
+        return;
+    __shared__ u64 s_off;
+    __shared__ u64 s_w[8];
+    const u32 nr = st->nr, c = blockIdx.x;
+    const u32 *cnt = st->rcnt[st->cur];
+    if (c < nr)
+    {
+        u64 part = 0;
+        for (u32 q = threadIdx.x; q < c; q += blockDim.x)
+            part += cnt[q];
+        // block sum (counts fit 32 bits per range; the sum may not)
+        for (int o = 16; o; o >>= 1)
+            part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+        if ((threadIdx.x & 31) == 0)
+            s_w[threadIdx.x >> 5] = part;
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            u64 t = 0;
+            for (int w = 0; w < 8; w++)
+                t += s_w[w];
+            s_off = t;
+        }
+        __syncthreads();
+        const u32 *src = st->tok[st->cur] + (u64)c * st->rcap;
+        u32 *dst = st->tok[st->cur ^ 1u] + s_off;
+        const u32 m = cnt[c];
+        for (u32 i = threadIdx.x; i < m; i += blockDim.x)
+            dst[i] = src[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        if (atomicAdd(&st->rp_done, 1u) == gridDim.x - 1)
+        {
+            st->rp_done = 0;
+            st->cur ^= 1u;
+            st->layout = LAYOUT_DENSE;
+        }
+    }
+}
+
+} // namespace bpe

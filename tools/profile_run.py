@@ -25,21 +25,29 @@ def main():
     ap.add_argument("--repeat", type=int, default=1)
     ap.add_argument("--encode", action="store_true")
     ap.add_argument("--profile-replace", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable)")
     args = ap.parse_args()
 
     import llmtokenizer_b200 as L
     from llmtokenizer_b200 import _lib
     corpus = _lib.load_corpus()
-    data = np.zeros(args.size, dtype=np.uint8)
-    assert corpus.gen_corpus_fill(args.kind, data.ctypes.data, data.size, args.seed,
-                                  50000 if args.kind == 0 else 65536) == 0
+    if args.kind == 2:  # uniform random bytes 1..255: every pair is rare, the passes are pure streaming
+        data = np.random.default_rng(args.seed).integers(1, 256, args.size, dtype=np.uint8)
+    else:
+        data = np.zeros(args.size, dtype=np.uint8)
+        assert corpus.gen_corpus_fill(args.kind, data.ctypes.data, data.size, args.seed,
+                                      50000 if args.kind == 0 else 65536) == 0
     ctx = L.Context(0)
     ctx.upload(data)
     if args.profile_replace:
         ctx.set_option("profile_replace", 1)
+    for o in args.opt:
+        k, v = o.split("=")
+        ctx.set_option(k, int(v))
     st = None
-    for _ in range(args.repeat):
+    for i in range(args.repeat):
         st = ctx.train(args.merges)
+        print(f"run {i}: ms_device {st['ms_device']:.2f} ms_total {st['ms_total']:.2f} replace_ms {st['replace_ms']:.2f} select_ms {st['select_ms']:.2f} apply_ms {st['apply_ms']:.2f} gap_ms {st['gap_ms']:.2f}", file=sys.stderr)
     out = {"train": {k: st[k] for k in ("n_input", "n_merges", "n_tokens", "kernel_launches", "replace_launches",
                                         "replace_bytes", "replace_ms", "ms_device", "table_capacity", "final_distinct")}}
     if st["replace_ms"] > 0:
