@@ -134,8 +134,12 @@ struct bpe_cuda_ctx
     // pair table (+ per-segment maxima of the hierarchical argmax)
     u64 *d_tkey = nullptr, *d_tmeta = nullptr;
     u64 tcap = 0;
-    SelPart *d_seg = nullptr;
-    u32 *d_seg_flag = nullptr, *d_seg_list = nullptr;
+    u32 *d_cflag = nullptr;  // candidate-membership bit per table slot
+    u32 *d_cand = nullptr;   // candidate slots of the argmax (fixed capacity)
+    SelPart *d_part = nullptr;
+    u32 cand_T = 0;          // host copy of the list threshold we asked for (0 = whole-table selection)
+    int want_ranged = 0;     // this run uses the streaming kernel (RANGED layout) for its a != b passes
+    u32 list_retry_below = ~0u; // whole-table mode: try a list again once the best count is below this
     // logs
     u32 *d_merges = nullptr;
     u64 *d_nhist = nullptr;
@@ -285,24 +289,22 @@ static int ensure_logs(bpe_cuda_ctx *c, size_t merges)
     return 0;
 }
 
+constexpr u32 CAND_CAP = 65536;
+
 struct TableMem
 {
     u64 *key = nullptr, *meta = nullptr;
-    SelPart *seg = nullptr;
-    u32 *seg_flag = nullptr, *seg_list = nullptr;
+    u32 *cflag = nullptr;
 };
 
 static int table_alloc(bpe_cuda_ctx *c, u64 cap, TableMem *t)
 {
-    const u64 nseg = cap >> SEG_SHIFT;
     CU(cudaMalloc(&t->key, cap * sizeof(u64)));
     CU(cudaMalloc(&t->meta, cap * sizeof(u64)));
-    CU(cudaMalloc(&t->seg, nseg * sizeof(SelPart)));
-    CU(cudaMalloc(&t->seg_flag, nseg * sizeof(u32)));
-    CU(cudaMalloc(&t->seg_list, nseg * sizeof(u32)));
+    CU(cudaMalloc(&t->cflag, cap / 8));
     CU(cudaMemsetAsync(t->key, 0xFF, cap * sizeof(u64), c->stream));
     CU(cudaMemsetAsync(t->meta, 0, cap * sizeof(u64), c->stream));
-    CU(cudaMemsetAsync(t->seg_flag, 0, nseg * sizeof(u32), c->stream));
+    CU(cudaMemsetAsync(t->cflag, 0, cap / 8, c->stream));
     return 0;
 }
 
@@ -310,21 +312,16 @@ static void table_free(bpe_cuda_ctx *c)
 {
     cudaFree(c->d_tkey);
     cudaFree(c->d_tmeta);
-    cudaFree(c->d_seg);
-    cudaFree(c->d_seg_flag);
-    cudaFree(c->d_seg_list);
+    cudaFree(c->d_cflag);
     c->d_tkey = c->d_tmeta = nullptr;
-    c->d_seg = nullptr;
-    c->d_seg_flag = c->d_seg_list = nullptr;
+    c->d_cflag = nullptr;
 }
 
 static void table_adopt(bpe_cuda_ctx *c, const TableMem &t, u64 cap)
 {
     c->d_tkey = t.key;
     c->d_tmeta = t.meta;
-    c->d_seg = t.seg;
-    c->d_seg_flag = t.seg_flag;
-    c->d_seg_list = t.seg_list;
+    c->d_cflag = t.cflag;
     c->tcap = cap;
 }
 
@@ -336,7 +333,7 @@ static int table_rehash(bpe_cuda_ctx *c, u64 new_cap)
         return rc;
     const int grid = (int)std::min<u64>((c->tcap + 255) / 256, (u64)c->sm_count * 8);
     rehash_kernel<<<grid, 256, 0, c->stream>>>(c->d_tkey, c->d_tmeta, c->tcap, t.key, t.meta, new_cap, &c->d_st->err);
-    table_swap_kernel<<<1, 1, 0, c->stream>>>(c->d_st, t.key, t.meta, new_cap, t.seg, t.seg_flag, t.seg_list);
+    table_swap_kernel<<<1, 1, 0, c->stream>>>(c->d_st, t.key, t.meta, new_cap, t.cflag);
     c->launches += 2;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
@@ -461,37 +458,76 @@ static int enqueue_census(bpe_cuda_ctx *c, u64 n_upper, int resolver)
     return 0;
 }
 
-// enqueue one merge step; z is the id the step will create if it runs
-static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool with_select, bool census = false,
-                        bool ranged = false)
+// ---- argmax candidates ---------------------------------------------------------------------------
+// (re)build the list of table slots whose count is >= T; T == 0 switches to whole-table selection
+static int rebuild_candidates(bpe_cuda_ctx *c, u32 T)
 {
-    prof_mark(c, PT_GAP);
-    if (with_select)
+    CU(cudaMemsetAsync(c->d_cflag, 0, c->tcap / 8, c->stream));
+    cand_reset_kernel<<<1, 1, 0, c->stream>>>(c->d_st);
+    c->launches++;
+    if (T)
     {
-        if (encode)
-            select_rank_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_delta_red);
-        else
-            select_kernel<<<c->sel_grid, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_delta_red);
+        const int grid = (int)std::min<u64>((c->tcap + 255) / 256, (u64)c->sm_count * 8);
+        cand_rebuild_kernel<<<grid, 256, 0, c->stream>>>(c->d_st, T);
         c->launches++;
-        if (census)
+    }
+    c->cand_T = T;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// Pick the threshold from the best count seen: the list then holds every pair within a factor two of
+// the maximum, and stays valid until the maximum itself has halved.  Tiny counts (many ties, lists as
+// long as the table) and overflowing lists fall back to whole-table selection.
+static int choose_candidates(bpe_cuda_ctx *c, u32 best)
+{
+    int rc;
+    if (best >= 8)
+    {
+        u32 T = best / 2;
+        for (int tries = 0; tries < 4 && T < best; tries++)
         {
-            int rc = enqueue_census(c, n_upper, 0);
-            if (rc)
+            if ((rc = rebuild_candidates(c, T)))
                 return rc;
-            c->stats.census_runs++;
+            if ((rc = poll_state(c)))
+                return rc;
+            if (!c->h_st->cand_overflow && c->h_st->ncand <= CAND_CAP / 2)
+                return 0;
+            T += (best - T + 1) / 2;
         }
     }
-    const bool hist = ((int)z + 1 <= c->smem_hist_max_vocab);
-    const size_t smem = replace_smem_bytes(hist, z);
-    int occ = c->replace_occ[0];
-    if (hist)
+    c->list_retry_below = best / 2;
+    if ((rc = rebuild_candidates(c, 0)))
+        return rc;
+    return poll_state(c);
+}
+
+// K2 alone (no deltas pending): start of a run, after a pause that did not commit a merge
+static int enqueue_select(bpe_cuda_ctx *c, bool encode)
+{
+    if (encode)
+        apply_select_kernel<<<1, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_delta_red, c->d_delta, 1);
+    else if (c->cand_T == 0)
+        select_kernel<<<c->sel_grid, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_part, c->d_delta_red);
+    else
+        apply_select_kernel<<<1, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_delta_red, c->d_delta, 0);
+    c->launches++;
+    return 0;
+}
+
+// One merge step for the committed merge that creates id z: [census] -> replace (+scan+deltas) ->
+// [edge record, ncclAllReduce] -> apply deltas + select the next merge.
+static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool census, bool ranged)
+{
+    prof_mark(c, PT_GAP);
+    if (census)
     {
-        const size_t per_sm = 220 * 1024;
-        occ = (int)std::max<size_t>(1, std::min<size_t>((size_t)occ, per_sm / (smem + 1024)));
+        int rc = enqueue_census(c, n_upper, 0);
+        if (rc)
+            return rc;
+        c->stats.census_runs++;
     }
-    const u64 tiles = std::max<u64>(1, (n_upper + R_TILE - 1) / R_TILE);
-    const int grid = (int)std::min<u64>(tiles, (u64)c->sm_count * (u64)occ);
-    prof_mark(c, PT_SELECT);
+    const bool hist = ((int)z + 1 <= c->smem_hist_max_vocab);
     if (ranged)
     {
         // RANGED stream, a != b: one CTA per range, no dependency between CTAs (a == b pauses the loop instead)
@@ -501,10 +537,22 @@ static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool w
         else
             replace_stream_kernel<false><<<c->rmax, V_THREADS, vsmem, c->stream>>>(c->d_st, c->d_delta);
     }
-    else if (hist)
-        replace_kernel<true><<<grid, R_THREADS, smem, c->stream>>>(c->d_st, c->d_desc, c->d_pdesc, c->d_delta);
     else
-        replace_kernel<false><<<grid, R_THREADS, smem, c->stream>>>(c->d_st, c->d_desc, c->d_pdesc, c->d_delta);
+    {
+        const size_t smem = replace_smem_bytes(hist, z);
+        int occ = c->replace_occ[0];
+        if (hist)
+        {
+            const size_t per_sm = 220 * 1024;
+            occ = (int)std::max<size_t>(1, std::min<size_t>((size_t)occ, per_sm / (smem + 1024)));
+        }
+        const u64 tiles = std::max<u64>(1, (n_upper + R_TILE - 1) / R_TILE);
+        const int grid = (int)std::min<u64>(tiles, (u64)c->sm_count * (u64)occ);
+        if (hist)
+            replace_kernel<true><<<grid, R_THREADS, smem, c->stream>>>(c->d_st, c->d_desc, c->d_pdesc, c->d_delta);
+        else
+            replace_kernel<false><<<grid, R_THREADS, smem, c->stream>>>(c->d_st, c->d_desc, c->d_pdesc, c->d_delta);
+    }
     prof_mark(c, PT_REPLACE);
     c->launches++;
     c->stats.replace_launches++;
@@ -515,20 +563,32 @@ static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool w
         NC(g_nccl.AllReduce(c->d_delta, c->d_delta_red, HDR_INTS + 4 * ((size_t)z + 1), ncclInt32, ncclSum, c->comm,
                             c->stream));
     }
-    const int agrid = (int)std::min<u64>((4ull * (z + 1) + 255) / 256, (u64)c->sm_count * 4);
-    apply_kernel<<<agrid, 256, 0, c->stream>>>(c->d_st, c->d_delta_red, c->d_delta);
-    c->launches++;
-    prof_mark(c, PT_APPLY);
+    if (encode || c->cand_T)
+    {
+        const int agrid = (int)std::min<u64>((4ull * (z + 1) + SEL_THREADS - 1) / SEL_THREADS, (u64)c->sm_count);
+        apply_select_kernel<<<agrid, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_delta_red, c->d_delta, encode ? 1 : 0);
+        c->launches++;
+        prof_mark(c, PT_APPLY);
+    }
+    else
+    {
+        const int agrid = (int)std::min<u64>((4ull * (z + 1) + 255) / 256, (u64)c->sm_count * 4);
+        apply_kernel<<<agrid, 256, 0, c->stream>>>(c->d_st, c->d_delta_red, c->d_delta);
+        prof_mark(c, PT_APPLY);
+        select_kernel<<<c->sel_grid, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_part, c->d_delta_red);
+        c->launches += 2;
+        prof_mark(c, PT_SELECT);
+    }
     return 0;
 }
 
-// Same-bucket ties / exact-threshold iterations.  (The exact chain-order resolver is launched
-// here; see resolver kernels.)
+// Same-bucket ties / exact-threshold iterations / layout changes / candidate rebuilds.
 static int resolve_pause(bpe_cuda_ctx *c, bool encode);
 
 static int run_loop(bpe_cuda_ctx *c, bool encode)
 {
     int rc;
+    c->list_retry_below = ~0u;
     if ((rc = poll_state(c)))
         return rc;
     for (;;)
@@ -545,28 +605,59 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
             continue;
         }
         const u64 m0 = h->merges_done;
-        const u64 z0 = 256 + m0;
+        if (!encode && m0 == 0 && !h->pending)
+        {
+            // the very first selection (whole table): its count sizes the candidate list
+            if ((rc = ensure_logs(c, 2)))
+                return rc;
+            if ((rc = enqueue_select(c, encode)))
+                return rc;
+            CU(cudaGetLastError());
+            if ((rc = poll_state(c)))
+                return rc;
+            if (c->h_st->stop == STOP_RUN && c->h_st->pending && (rc = choose_candidates(c, c->h_st->freq)))
+                return rc;
+            if (c->h_st->merges_done == 0)
+                continue; // stopped or paused before committing anything
+        }
+        h = c->h_st;
+        const u64 m1 = h->merges_done;
+        const u64 z0 = 256 + m1 - (h->pending ? 1 : 0); // id created by the first pass of this batch
         // batch size: bounded by the table headroom it may consume (<= 2*(V+1) new keys a step)
         u64 G = (u64)std::max(1, c->batch_steps);
-        if (!encode && h->max_merges != ~0ull && h->max_merges >= m0)
-            G = std::min<u64>(G, h->max_merges - m0 + 1);
+        if (!encode && h->max_merges != ~0ull && h->max_merges >= m1)
+            G = std::min<u64>(G, h->max_merges - m1 + 1);
         if (encode)
-            G = std::min<u64>(G, h->enc_total - m0 + 1);
+            G = std::min<u64>(G, h->enc_total - m1 + 1);
         while (G > 4 && G * 2 * (z0 + G + 1) > c->tcap / 4)
             G /= 2;
         const u64 margin = G * 2 * (z0 + G + 1);
         if (h->occupied + margin > c->tcap / 2 + c->tcap / 8)
         {
             u64 want = 1ull << 20;
-            while (want < 4 * ((u64)h->distinct + margin))
+            while (want < 3 * ((u64)h->distinct + margin))
                 want *= 2;
             if ((rc = table_rehash(c, want)))
                 return rc;
+            if (c->cand_T && (rc = choose_candidates(c, std::max<u32>(h->freq, 2 * c->cand_T))))
+                return rc;
+            h = c->h_st;
         }
-        if ((rc = ensure_delta(c, (size_t)(z0 + G + 1))))
+        if ((rc = ensure_delta(c, (size_t)(z0 + G + 2))))
             return rc;
-        if ((rc = ensure_logs(c, (size_t)(m0 + G + 1))))
+        if ((rc = ensure_logs(c, (size_t)(m1 + G + 2))))
             return rc;
+        // candidate list upkeep: try a list when selection runs on the whole table, shrink a bloated one
+        if (!encode)
+        {
+            if (c->cand_T == 0 && h->freq >= 16 && h->freq < c->list_retry_below)
+                rc = choose_candidates(c, h->freq);
+            else if (c->cand_T && (h->cand_overflow || h->ncand > CAND_CAP * 3 / 4))
+                rc = choose_candidates(c, std::max<u32>(h->freq, c->cand_T + 1));
+            if (rc)
+                return rc;
+            h = c->h_st;
+        }
         // Worker-table growth is only possible while some slice can still hold thr(B_t) distinct pairs.
         bool census = false;
         if (!encode && c->world == 1)
@@ -586,7 +677,7 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
         }
         // The streaming kernel works on the RANGED layout; everything that needs positions in one dense
         // array (static regime, census) keeps the stream dense and uses the general kernel.
-        const bool ranged = c->use_stream && !census && !h->static_mode && h->n_global >= STATIC_LIMIT && h->n > 0;
+        const bool ranged = c->want_ranged && !census && !h->static_mode && h->n > 0;
         if (ranged && h->layout == LAYOUT_DENSE)
         {
             partition_kernel<<<1, RANGE_MAX, 0, c->stream>>>(c->d_st);
@@ -597,8 +688,10 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
             repack_kernel<<<RANGE_MAX, 256, 0, c->stream>>>(c->d_st);
             c->launches++;
         }
+        if (!h->pending && (rc = enqueue_select(c, encode)))
+            return rc;
         for (u64 g = 0; g < G; g++)
-            if ((rc = enqueue_step(c, (u32)(z0 + g), h->n, encode, true, census, ranged)))
+            if ((rc = enqueue_step(c, (u32)(z0 + g), h->n, encode, census, ranged)))
                 return rc;
         CU(cudaGetLastError());
         if ((rc = poll_state(c)))
@@ -630,11 +723,10 @@ static int init_state(bpe_cuda_ctx *c, u64 n_local, u64 max_merges, bool encode,
     s.tkey = c->d_tkey;
     s.tmeta = c->d_tmeta;
     s.tcap = c->tcap;
-    s.seg = c->d_seg;
-    s.seg_flag = c->d_seg_flag;
-    s.seg_list = c->d_seg_list;
-    s.nseg = c->tcap >> SEG_SHIFT;
-    s.all_dirty = 1;
+    s.cand = c->d_cand;
+    s.cflag = c->d_cflag;
+    s.cand_cap = CAND_CAP;
+    s.cand_T = 0;
     s.halo_before[0] = s.halo_before[1] = SENT;
     s.halo_after[0] = s.halo_after[1] = s.halo_after[2] = SENT;
     s.rank = (u32)c->rank;
@@ -647,6 +739,8 @@ static int init_state(bpe_cuda_ctx *c, u64 n_local, u64 max_merges, bool encode,
     s.enc_total = enc_total;
     s.static_mode = 0;
     s.use_stream = (u32)c->use_stream;
+    c->want_ranged = c->use_stream && !c->force_census && (u64)c->n_bytes * (u64)c->world >= STATIC_LIMIT;
+    s.want_ranged = (u32)c->want_ranged;
     s.layout = s.layout_next = LAYOUT_DENSE;
     s.rmax = (u32)c->rmax;
     for (int i = 0; i < 2; i++)
@@ -687,6 +781,12 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
         }
     c->rmax = std::min(RANGE_MAX, c->sm_count * c->stream_occ[0]);
     c->sel_grid = c->sm_count * 2;
+    if (!c->d_part)
+    {
+        CU(cudaMalloc(&c->d_part, (size_t)c->sel_grid * sizeof(SelPart)));
+        CU(cudaMalloc(&c->d_cand, CAND_CAP * sizeof(u32)));
+    }
+    c->cand_T = 0;
     // fresh table
     table_free(c);
     {
@@ -863,47 +963,61 @@ static int resolve_pause(bpe_cuda_ctx *c, bool encode)
 {
     DevState *h = c->h_st;
     int rc;
+    const u32 pause = h->pause;
+    const u64 merges_done = h->merges_done, n = h->n;
+    const u32 best = (u32)(h->sel_key >> 32);
+    if (pause & PAUSE_REBUILD)
+    {
+        // nothing was committed: new list (or whole-table mode), then select again
+        if ((rc = choose_candidates(c, best)))
+            return rc;
+        resume_kernel<<<1, 1, 0, c->stream>>>(c->d_st);
+        c->launches++;
+        return 0;
+    }
     if (h->layout == LAYOUT_RANGED)
     {
         // everything below works on positions of one dense array
         repack_kernel<<<RANGE_MAX, 256, 0, c->stream>>>(c->d_st);
         c->launches++;
     }
-    if (h->pause & PAUSE_SAME)
+    if (pause & PAUSE_SAME)
     {
         // the merge (a == a) is already committed: run its pass with the general kernel
         resume_kernel<<<1, 1, 0, c->stream>>>(c->d_st);
         c->launches++;
-        if ((rc = ensure_delta(c, (size_t)(256 + h->merges_done + 2))))
+        if ((rc = ensure_delta(c, (size_t)(256 + merges_done + 2))))
             return rc;
-        return enqueue_step(c, (u32)(256 + h->merges_done - 1), h->n, encode, false);
+        if ((rc = ensure_logs(c, (size_t)(merges_done + 2))))
+            return rc;
+        return enqueue_step(c, (u32)(256 + merges_done - 1), n, encode, false, false);
     }
-    if (h->pause & PAUSE_STATIC)
+    if (pause & PAUSE_STATIC)
     {
-        // the select kernel latched static_mode; nothing else to do but resume
+        // the select kernel latched static_mode; nothing else to do but resume (and select again)
         resume_kernel<<<1, 1, 0, c->stream>>>(c->d_st);
         c->launches++;
         return 0;
     }
     c->stats.resolver_runs++;
-    if ((rc = ensure_delta(c, (size_t)(256 + h->merges_done + 2))))
+    if ((rc = ensure_delta(c, (size_t)(256 + merges_done + 2))))
         return rc;
-    if ((rc = ensure_logs(c, (size_t)(h->merges_done + 2))))
+    if ((rc = ensure_logs(c, (size_t)(merges_done + 2))))
         return rc;
     if (c->world > 1)
     {
         // sharded stream: chain order is taken from the table order (documented limitation; counted)
         tier_a_commit_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_delta_red);
         c->launches++;
-        return enqueue_step(c, (u32)(256 + h->merges_done), h->n, encode, false);
+        return enqueue_step(c, (u32)(256 + merges_done), n, encode, false, false);
     }
-    const u32 slices = (h->n < STATIC_LIMIT) ? REF_THREADS : 1;
-    if ((rc = ensure_resolver(c, h->n, slices)))
+    const u32 slices = (n < STATIC_LIMIT) ? REF_THREADS : 1;
+    if ((rc = ensure_resolver(c, n, slices)))
         return rc;
-    if ((rc = enqueue_census(c, h->n, 1)))
+    if ((rc = enqueue_census(c, n, 1)))
         return rc;
-    const int g = pos_grid(c, h->n);
-    const int tg = (int)std::max<u64>(1, std::min<u64>(h->n / SCAN_TILE + 1, (u64)c->sm_count * 8));
+    const int g = pos_grid(c, n);
+    const int tg = (int)std::max<u64>(1, std::min<u64>(n / SCAN_TILE + 1, (u64)c->sm_count * 8));
     const int sg = (int)std::min<u64>((c->tcap + 255) / 256, (u64)c->sm_count * 8);
     rank_tile_count_kernel<<<tg, 256, 0, c->stream>>>(c->d_rs, c->d_first, c->d_pos_slot, c->d_tile_cnt);
     rank_tile_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_rs, c->d_tile_cnt, c->d_tile_off);
@@ -916,7 +1030,7 @@ static int resolve_pause(bpe_cuda_ctx *c, bool encode)
     resolver_commit_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_rs, c->d_delta_red);
     c->launches += 9;
     CU(cudaGetLastError());
-    return enqueue_step(c, (u32)(256 + h->merges_done), h->n, encode, false);
+    return enqueue_step(c, (u32)(256 + merges_done), n, encode, false, false);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1018,6 +1132,8 @@ void bpe_cuda_ctx_destroy(bpe_cuda_ctx_t *c)
     if (c->d_delta_red != c->d_delta)
         cudaFree(c->d_delta_red);
     table_free(c);
+    cudaFree(c->d_part);
+    cudaFree(c->d_cand);
     cudaFree(c->d_merges);
     cudaFree(c->d_nhist);
     cudaFree(c->d_enc_merges);

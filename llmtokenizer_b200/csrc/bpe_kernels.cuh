@@ -42,7 +42,8 @@ enum : u32
     PAUSE_TIE = 1,    // >= 2 maximal pairs share the winning bucket: chain order decides
     PAUSE_EDGE = 2,   // D sits exactly on a doubling threshold of the merged table
     PAUSE_STATIC = 4, // stream fell below 1,048,576 tokens: reference switches to static slicing
-    PAUSE_SAME = 8    // a == b was selected (and committed) while the stream is RANGED: needs the general kernel
+    PAUSE_SAME = 8,   // a == b was selected (and committed) while the stream is RANGED: needs the general kernel
+    PAUSE_REBUILD = 16 // the best candidate fell below the list's threshold: the list must be rebuilt
 };
 enum : u32
 {
@@ -61,7 +62,6 @@ enum : u32
 
 // Device-resident control block.  Everything a merge step needs lives here, so a step is a fixed
 // sequence of launches with no host round trip.
-struct SelPart;
 struct DevState
 {
     // token stream, ping-pong (pointers are 16 B aligned; 4 readable slots in front of each)
@@ -82,6 +82,7 @@ struct DevState
     // independently (one CTA each, no prefix scan across CTAs): range c lives at tok[buf][c*rcap ..
     // c*rcap + rcnt[buf][c]); redge[buf][8c..] holds its first three and last two tokens.
     u32 layout, layout_next;
+    u32 want_ranged, pad_wr; // the host runs a != b passes with the streaming kernel: a == b must pause first
     u32 nr, rmax;
     u64 rcap;
     u32 *rcnt[2];
@@ -93,14 +94,13 @@ struct DevState
     u64 tcap;
     i64 distinct; // D: keys with count > 0
     u64 occupied; // claimed slots (dead keys included)
-    // segment maxima over the table (hierarchical argmax): only segments touched since the last
-    // selection are rescanned
-    struct SelPart *seg;
-    u32 *seg_flag;
-    u32 *seg_list;
-    u64 nseg;
-    u64 sel_B; // bucket count the segment maxima were computed for
-    u32 n_dirty, all_dirty;
+    // argmax candidates: every table slot whose count is >= cand_T is in cand[] (cflag = membership
+    // bits), so the maximum over cand[] is the maximum over the table.  cand_T == 0: no list, the
+    // selection scans the whole table.
+    u32 *cand;
+    u32 *cflag;
+    u32 ncand, cand_cap, cand_T, cand_overflow;
+    u32 pending, pad_pend; // a merge is committed and its pass / delta application is still to come
     // scheduling counters
     u32 ticket, sel_done;
     // selection result (kept for the resolver)
@@ -405,18 +405,15 @@ __global__ void rehash_kernel(const u64 *__restrict__ okey, const u64 *__restric
     }
 }
 
-__global__ void table_swap_kernel(DevState *st, u64 *nkey, u64 *nmeta, u64 ncap, SelPart *seg, u32 *seg_flag, u32 *seg_list)
+__global__ void table_swap_kernel(DevState *st, u64 *nkey, u64 *nmeta, u64 ncap, u32 *cflag)
 {
     st->tkey = nkey;
     st->tmeta = nmeta;
     st->tcap = ncap;
+    st->cflag = cflag;
     st->occupied = (u64)st->distinct;
-    st->seg = seg;
-    st->seg_flag = seg_flag;
-    st->seg_list = seg_list;
-    st->nseg = ncap >> 10;
-    st->n_dirty = 0;
-    st->all_dirty = 1;
+    st->ncand = 0;
+    st->cand_T = 0; // slots moved: the host rebuilds the candidate list
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -669,6 +666,7 @@ __device__ inline void commit_merge(DevState *st, u32 a, u32 b, u32 freq, const 
     if (!encode && st->n_global >= STATIC_LIMIT)
         dynamic_regime_census(st, rec_all);
     st->n_next = 0; // the ranged streaming kernel accumulates its ranges' new lengths here
+    st->pending = 1;
     st->n_hist[k] = st->n_global;
     st->merges_done = k + 1;
     st->epoch = st->epoch + 1;
@@ -676,85 +674,12 @@ __device__ inline void commit_merge(DevState *st, u32 a, u32 b, u32 freq, const 
 }
 
 constexpr int SEL_THREADS = 512;
-constexpr int SEG_SHIFT = 10; // 1,024 slots (8 KB of meta) per segment
-constexpr u64 SEG_SLOTS = 1ull << SEG_SHIFT;
 
-__device__ __forceinline__ void mark_dirty(DevState *st, u64 slot)
+// The decision once the best packed key (count << 32 | ~bucket), its multiplicity and a slot holding
+// it are known: stop / pause / commit (bpe.c:730-758).  One thread.
+__device__ inline void decide(DevState *st, u64 k, u64 s, u32 m, const int32_t *delta_reduced)
 {
-    const u32 seg = (u32)(slot >> SEG_SHIFT);
-    if (atomicExch(&st->seg_flag[seg], 1u) == 0u)
-        st->seg_list[atomicAdd(&st->n_dirty, 1u)] = seg;
-}
-
-// Phase 1 (all blocks): recompute the maximum of every segment of the table that the last merge
-// touched (all of them when the bucket count B(D) changed or the table was rebuilt).
-// Phase 2 (last block to finish): fold the per-segment maxima and decide.
-__global__ void __launch_bounds__(SEL_THREADS) select_kernel(DevState *st, const int32_t *delta_reduced)
-{
-    if (st->stop != STOP_RUN)
-        return;
-    __shared__ SelPart sm[SEL_THREADS / 32];
-    __shared__ bool s_last;
-    const u64 *__restrict__ meta = st->tmeta;
     const u64 D = (u64)st->distinct;
-    const u64 B = merged_buckets(D);
-    const u32 bmask = (u32)(B - 1);
-    SelPart *segp = st->seg;
-    const u64 nseg = st->nseg;
-    const bool all = st->all_dirty || (B != st->sel_B);
-    const u64 nwork = all ? nseg : (u64)st->n_dirty;
-    u64 k, s;
-    u32 m;
-    for (u64 w = blockIdx.x; w < nwork; w += gridDim.x)
-    {
-        const u64 seg = all ? w : (u64)st->seg_list[w];
-        k = 0;
-        s = NO_SLOT;
-        m = 0;
-        for (u32 j = threadIdx.x; j < SEG_SLOTS; j += SEL_THREADS)
-        {
-            const u64 i = (seg << SEG_SHIFT) + j;
-            const u64 mv = meta[i];
-            if (mv >> 32)
-            {
-                const u64 kk = (mv & 0xFFFFFFFF00000000ull) | (u64)(0xFFFFFFFFu - ((u32)mv & bmask));
-                sel_combine(k, s, m, kk, i, 1u);
-            }
-        }
-        sel_block_reduce(k, s, m, sm);
-        if (threadIdx.x == 0)
-        {
-            segp[seg].key = k;
-            segp[seg].slot = s;
-            segp[seg].mult = m;
-            st->seg_flag[seg] = 0;
-        }
-    }
-    if (threadIdx.x == 0)
-    {
-        __threadfence();
-        const u32 done = atomicAdd(&st->sel_done, 1u);
-        s_last = (done == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last)
-        return;
-    __threadfence();
-    k = 0;
-    s = NO_SLOT;
-    m = 0;
-    for (u64 i = threadIdx.x; i < nseg; i += blockDim.x)
-    {
-        const volatile SelPart *p = segp + i;
-        sel_combine(k, s, m, p->key, p->slot, p->mult);
-    }
-    sel_block_reduce(k, s, m, sm);
-    if (threadIdx.x != 0)
-        return;
-    st->sel_done = 0;
-    st->n_dirty = 0;
-    st->all_dirty = 0;
-    st->sel_B = B;
     st->sel_key = k;
     st->sel_slot = s;
     st->sel_mult = m;
@@ -769,6 +694,14 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(DevState *st, const
     else
         st->n_global = st->n;
     const u32 freq = (u32)(k >> 32);
+    if (st->cand_T && D != 0 && freq < st->cand_T && st->merges_done < st->max_merges)
+    {
+        // every count >= cand_T is in the list, and nothing in the list reaches cand_T any more:
+        // the true maximum is somewhere below; the host rebuilds the list with a lower threshold
+        st->pause = PAUSE_REBUILD;
+        st->stop = STOP_PAUSE;
+        return;
+    }
     if (D == 0 || m == 0 || freq <= 1 || st->merges_done >= st->max_merges) // bpe.c:730, bpe.c:745, cap
     {
         st->stop = STOP_DONE;
@@ -794,7 +727,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(DevState *st, const
     }
     const u64 key = st->tkey[s];
     commit_merge(st, (u32)(key & 0xFFFFFFFFull), (u32)(key >> 32), freq, rec_all);
-    if (st->a == st->b && st->layout == LAYOUT_RANGED)
+    if (st->a == st->b && st->want_ranged && !st->static_mode)
     {
         // run-parity pairing needs the general kernel on a dense stream: the host repacks, then resumes
         st->pause = PAUSE_SAME;
@@ -803,11 +736,9 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(DevState *st, const
 }
 
 // encode: the "selection" is simply the next rank of the given merge list; a rank whose pair does
-// not occur (count 0 in the replicated table) costs no pass
-__global__ void select_rank_kernel(DevState *st, const int32_t *delta_reduced)
+// not occur (count 0 in the replicated table) costs no pass.  One thread.
+__device__ inline void decide_rank(DevState *st, const int32_t *delta_reduced)
 {
-    if (st->stop != STOP_RUN)
-        return;
     const u64 r = st->merges_done;
     if (r >= st->enc_total)
     {
@@ -824,12 +755,71 @@ __global__ void select_rank_kernel(DevState *st, const int32_t *delta_reduced)
     else
     {
         st->ranks_applied++;
-        if (a == b && st->layout == LAYOUT_RANGED)
+        if (a == b && st->want_ranged && !st->static_mode)
         {
             st->pause = PAUSE_SAME;
             st->stop = STOP_PAUSE;
         }
     }
+}
+
+// K2, whole-table form (no candidate list: start of training, tiny counts near exhaustion).
+__global__ void __launch_bounds__(SEL_THREADS) select_kernel(DevState *st, SelPart *part, const int32_t *delta_reduced)
+{
+    if (st->stop != STOP_RUN || st->pending)
+        return;
+    __shared__ SelPart sm[SEL_THREADS / 32];
+    __shared__ bool s_last;
+    const u64 cap = st->tcap;
+    const u64 *__restrict__ meta = st->tmeta;
+    const u64 D = (u64)st->distinct;
+    const u64 B = merged_buckets(D);
+    const u32 bmask = (u32)(B - 1);
+    u64 k = 0, s = NO_SLOT;
+    u32 m = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x)
+    {
+        const u64 mv = meta[i];
+        if (mv >> 32)
+        {
+            const u64 kk = (mv & 0xFFFFFFFF00000000ull) | (u64)(0xFFFFFFFFu - ((u32)mv & bmask));
+            sel_combine(k, s, m, kk, i, 1u);
+        }
+    }
+    sel_block_reduce(k, s, m, sm);
+    if (threadIdx.x == 0)
+    {
+        part[blockIdx.x].key = k;
+        part[blockIdx.x].slot = s;
+        part[blockIdx.x].mult = m;
+        __threadfence();
+        const u32 done = atomicAdd(&st->sel_done, 1u);
+        s_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last)
+        return;
+    __threadfence();
+    k = 0;
+    s = NO_SLOT;
+    m = 0;
+    for (u32 i = threadIdx.x; i < gridDim.x; i += blockDim.x)
+    {
+        const volatile SelPart *p = part + i;
+        sel_combine(k, s, m, p->key, p->slot, p->mult);
+    }
+    sel_block_reduce(k, s, m, sm);
+    if (threadIdx.x != 0)
+        return;
+    st->sel_done = 0;
+    decide(st, k, s, m, delta_reduced);
+}
+
+__global__ void select_rank_kernel(DevState *st, const int32_t *delta_reduced)
+{
+    if (st->stop != STOP_RUN || st->pending)
+        return;
+    decide_rank(st, delta_reduced);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1202,18 +1192,39 @@ __global__ void __launch_bounds__(R_THREADS) replace_kernel(DevState *st, u64 *d
 
 // ---------------------------------------------------------------------------------------------
 // K4: fold the (all-reduced) delta vectors into the replicated pair table, zero the merged pair,
-// keep D exact, flip the ping-pong buffers.
-__global__ void __launch_bounds__(256) apply_kernel(DevState *st, int32_t *delta_in, int32_t *delta_local)
+// keep D exact and the candidate list complete.
+__device__ __forceinline__ void cand_offer(DevState *st, u64 slot, u32 newcount)
 {
-    if (st->stop != STOP_RUN)
+    const u32 T = st->cand_T;
+    if (!T || newcount < T)
         return;
-    const u32 gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (st->skip)
-        return;
+    const u32 bit = 1u << (slot & 31);
+    if (atomicOr(&st->cflag[slot >> 5], bit) & bit)
+        return; // already listed
+    const u32 i = atomicAdd(&st->ncand, 1u);
+    if (i < st->cand_cap)
+        st->cand[i] = (u32)slot;
+    else
+        st->cand_overflow = 1;
+}
+
+__device__ inline void apply_deltas(DevState *st, int32_t *delta_in, int32_t *delta_local, u32 gtid, u32 gsize)
+{
     const u32 a = st->a, b = st->b, z = st->z;
     const u32 total = 4 * (z + 1);
     u64 *tmeta = st->tmeta;
-    for (u32 i = gtid; i < total; i += gridDim.x * blockDim.x)
+    if (gtid == gsize - 1)
+    {
+        // the merged pair is gone (its own thread, so the probe overlaps the others)
+        const u64 s = table_find(st->tkey, st->tcap, (u64)a | ((u64)b << 32), murmur3_pair(a, b));
+        if (s != NO_SLOT)
+        {
+            const u32 old = atomicExch(cnt_ptr(tmeta, s), 0u);
+            if (old)
+                atomicAdd(reinterpret_cast<u64 *>(&st->distinct), ~0ull);
+        }
+    }
+    for (u32 i = gtid; i < total; i += gsize)
     {
         const int32_t d = delta_in[HDR_INTS + i];
         if (delta_local != delta_in)
@@ -1256,7 +1267,7 @@ __global__ void __launch_bounds__(256) apply_kernel(DevState *st, int32_t *delta
             const u32 old = atomicAdd(cnt_ptr(tmeta, s), (u32)d);
             if (old == 0)
                 atomicAdd(reinterpret_cast<u64 *>(&st->distinct), 1ull);
-            mark_dirty(st, s);
+            cand_offer(st, s, old + (u32)d);
         }
         else
         {
@@ -1271,23 +1282,125 @@ __global__ void __launch_bounds__(256) apply_kernel(DevState *st, int32_t *delta
                 atomicOr(&st->err, ERR_NEGATIVE);
             if (old == (u32)d)
                 atomicAdd(reinterpret_cast<u64 *>(&st->distinct), ~0ull); // -1
-            mark_dirty(st, s);
         }
     }
-    if (gtid == 0)
+}
+
+// the pass is over: its output becomes the current stream (one thread, after every delta is applied)
+__device__ __forceinline__ void finish_pass(DevState *st)
+{
+    if (!st->skip)
     {
-        const u64 s = table_find(st->tkey, st->tcap, (u64)a | ((u64)b << 32), murmur3_pair(a, b));
-        if (s != NO_SLOT)
-        {
-            const u32 old = atomicExch(cnt_ptr(tmeta, s), 0u); // the merged pair is gone
-            if (old)
-                atomicAdd(reinterpret_cast<u64 *>(&st->distinct), ~0ull);
-            mark_dirty(st, s);
-        }
         st->n = st->n_next;
         st->cur ^= 1u;
         st->layout = st->layout_next;
     }
+    st->pending = 0;
+}
+
+// whole-table mode: K4 alone (select_kernel follows)
+__global__ void __launch_bounds__(256) apply_kernel(DevState *st, int32_t *delta_in, int32_t *delta_local)
+{
+    if (st->stop != STOP_RUN || !st->pending)
+        return;
+    if (!st->skip)
+        apply_deltas(st, delta_in, delta_local, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        if (atomicAdd(&st->sel_done, 1u) == gridDim.x - 1)
+        {
+            st->sel_done = 0;
+            finish_pass(st);
+        }
+    }
+}
+
+// list mode: K4 + K2 in one launch.  Every block applies its share of the deltas; the last block to
+// finish then owns a consistent table, takes the maximum over the candidate list (one gather per
+// candidate, warp shuffles + block tree with the multiplicity of the maximal key carried along) and
+// decides.  encode: the next rank of the given merge list instead of the maximum.
+__global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st, int32_t *delta_in, int32_t *delta_local, int encode)
+{
+    if (st->stop != STOP_RUN)
+        return;
+    __shared__ SelPart sm[SEL_THREADS / 32];
+    __shared__ bool s_last;
+    const bool pending = st->pending != 0;
+    if (pending && !st->skip)
+        apply_deltas(st, delta_in, delta_local, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        s_last = atomicAdd(&st->sel_done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last)
+        return;
+    __threadfence();
+    if (threadIdx.x == 0)
+    {
+        st->sel_done = 0;
+        if (pending)
+            finish_pass(st);
+    }
+    __syncthreads();
+    if (encode)
+    {
+        if (threadIdx.x == 0)
+            decide_rank(st, delta_in);
+        return;
+    }
+    const volatile u64 *meta = st->tmeta;
+    const u64 D = (u64) * reinterpret_cast<volatile i64 *>(&st->distinct);
+    const u64 B = merged_buckets(D);
+    const u32 bmask = (u32)(B - 1);
+    const u32 ncr = *reinterpret_cast<volatile u32 *>(&st->ncand);
+    const u32 nc = ncr < st->cand_cap ? ncr : st->cand_cap;
+    const u32 *cand = st->cand;
+    u64 k = 0, s = NO_SLOT;
+    u32 m = 0;
+    for (u32 i = threadIdx.x; i < nc; i += SEL_THREADS)
+    {
+        const u64 slot = *reinterpret_cast<const volatile u32 *>(cand + i);
+        const u64 mv = meta[slot];
+        if (mv >> 32)
+        {
+            const u64 kk = (mv & 0xFFFFFFFF00000000ull) | (u64)(0xFFFFFFFFu - ((u32)mv & bmask));
+            sel_combine(k, s, m, kk, slot, 1u);
+        }
+    }
+    sel_block_reduce(k, s, m, sm);
+    if (threadIdx.x == 0)
+        decide(st, k, s, m, delta_in);
+}
+
+__global__ void cand_reset_kernel(DevState *st)
+{
+    st->ncand = 0;
+    st->cand_overflow = 0;
+    st->cand_T = 0;
+}
+
+// (re)build the candidate list for threshold T (cflag cleared by the host, then cand_reset_kernel)
+__global__ void __launch_bounds__(256) cand_rebuild_kernel(DevState *st, u32 T)
+{
+    const u64 cap = st->tcap;
+    const u64 *__restrict__ meta = st->tmeta;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x)
+        if ((u32)(meta[i] >> 32) >= T)
+        {
+            atomicOr(&st->cflag[i >> 5], 1u << (i & 31));
+            const u32 j = atomicAdd(&st->ncand, 1u);
+            if (j < st->cand_cap)
+                st->cand[j] = (u32)i;
+            else
+                st->cand_overflow = 1;
+        }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        st->cand_T = T;
 }
 
 // halos of the untouched stream (before the first merge), for the shard-straddling byte pair

@@ -164,6 +164,12 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
         return;
     const u32 a = st->a, b = st->b, z = st->z;
     const u32 cta = blockIdx.x, nr = st->nr;
+    if (a == b || st->layout != LAYOUT_RANGED)
+    {
+        if (threadIdx.x == 0)
+            atomicOr(&st->err, ERR_PROBE); // host logic error: this kernel only takes a != b passes of a RANGED stream
+        return;
+    }
     if (cta >= nr)
         return;
     const u32 ibuf = st->cur, obuf = st->cur ^ 1u;
