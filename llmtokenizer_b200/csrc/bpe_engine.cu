@@ -119,7 +119,10 @@ struct bpe_cuda_ctx
     size_t tok_cap = 0;
     // control block
     DevState *d_st = nullptr;
-    DevState *h_st = nullptr; // pinned
+    DevState *h_st = nullptr;              // the latest copy of the control block (one of h_buf)
+    DevState *h_buf[2] = {nullptr, nullptr}; // pinned
+    cudaEvent_t poll_ev[2] = {nullptr, nullptr};
+    int speculate = 1;                       // enqueue the next batch before the current one has been polled
     // ranged layout: per buffer, length and edge tokens of every range
     u32 *d_rcnt[2] = {nullptr, nullptr};
     u32 *d_redge[2] = {nullptr, nullptr};
@@ -135,6 +138,14 @@ struct bpe_cuda_ctx
     u64 *d_tkey = nullptr, *d_tmeta = nullptr;
     u64 tcap = 0;
     u32 *d_cflag = nullptr;  // candidate-membership bit per table slot
+    struct Arena
+    {
+        u64 *key = nullptr, *meta = nullptr;
+        u32 *cflag = nullptr;
+        u64 cap = 0;
+    } arena[2];
+    int arena_cur = 0;
+    double host_ms[6] = {0, 0, 0, 0, 0, 0}; // wall clock of host-side phases (debug): rehash, candidates, pause, poll wait, enqueue, setup
     u32 *d_cand = nullptr;   // candidate slots of the argmax (fixed capacity)
     SelPart *d_part = nullptr;
     u32 cand_T = 0;          // host copy of the list threshold we asked for (0 = whole-table selection)
@@ -181,6 +192,14 @@ struct bpe_cuda_ctx
 };
 
 static inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+struct HostTimer
+{
+    double *acc;
+    std::chrono::steady_clock::time_point t0;
+    explicit HostTimer(double *a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+    ~HostTimer() { *acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
 
 static int ensure_bytes(bpe_cuda_ctx *c, size_t n)
 {
@@ -291,73 +310,95 @@ static int ensure_logs(bpe_cuda_ctx *c, size_t merges)
 
 constexpr u32 CAND_CAP = 65536;
 
-struct TableMem
-{
-    u64 *key = nullptr, *meta = nullptr;
-    u32 *cflag = nullptr;
-};
+// Pair-table memory comes from two arenas that only ever grow and live as long as the context: a
+// rehash builds the new table in the arena the current one does not use.  (cudaMalloc / cudaFree
+// inside a run cost milliseconds and synchronise the device.)
+typedef bpe_cuda_ctx::Arena TableMem;
 
-static int table_alloc(bpe_cuda_ctx *c, u64 cap, TableMem *t)
+static int table_alloc(bpe_cuda_ctx *c, u64 cap, int arena)
 {
-    CU(cudaMalloc(&t->key, cap * sizeof(u64)));
-    CU(cudaMalloc(&t->meta, cap * sizeof(u64)));
-    CU(cudaMalloc(&t->cflag, cap / 8));
-    CU(cudaMemsetAsync(t->key, 0xFF, cap * sizeof(u64), c->stream));
-    CU(cudaMemsetAsync(t->meta, 0, cap * sizeof(u64), c->stream));
-    CU(cudaMemsetAsync(t->cflag, 0, cap / 8, c->stream));
+    TableMem &t = c->arena[arena];
+    if (t.cap < cap)
+    {
+        cudaFree(t.key);
+        cudaFree(t.meta);
+        cudaFree(t.cflag);
+        t = TableMem();
+        CU(cudaMalloc(&t.key, cap * sizeof(u64)));
+        CU(cudaMalloc(&t.meta, cap * sizeof(u64)));
+        CU(cudaMalloc(&t.cflag, cap / 8));
+        t.cap = cap;
+    }
+    CU(cudaMemsetAsync(t.key, 0xFF, cap * sizeof(u64), c->stream));
+    CU(cudaMemsetAsync(t.meta, 0, cap * sizeof(u64), c->stream));
+    CU(cudaMemsetAsync(t.cflag, 0, cap / 8, c->stream));
     return 0;
 }
 
 static void table_free(bpe_cuda_ctx *c)
 {
-    cudaFree(c->d_tkey);
-    cudaFree(c->d_tmeta);
-    cudaFree(c->d_cflag);
+    for (int i = 0; i < 2; i++)
+    {
+        cudaFree(c->arena[i].key);
+        cudaFree(c->arena[i].meta);
+        cudaFree(c->arena[i].cflag);
+        c->arena[i] = TableMem();
+    }
     c->d_tkey = c->d_tmeta = nullptr;
     c->d_cflag = nullptr;
 }
 
-static void table_adopt(bpe_cuda_ctx *c, const TableMem &t, u64 cap)
+static void table_adopt(bpe_cuda_ctx *c, int arena, u64 cap)
 {
-    c->d_tkey = t.key;
-    c->d_tmeta = t.meta;
-    c->d_cflag = t.cflag;
+    c->arena_cur = arena;
+    c->d_tkey = c->arena[arena].key;
+    c->d_tmeta = c->arena[arena].meta;
+    c->d_cflag = c->arena[arena].cflag;
     c->tcap = cap;
 }
 
 static int table_rehash(bpe_cuda_ctx *c, u64 new_cap)
 {
-    TableMem t;
-    int rc = table_alloc(c, new_cap, &t);
+    HostTimer ht(&c->host_ms[0]);
+    const int other = c->arena_cur ^ 1;
+    int rc = table_alloc(c, new_cap, other);
     if (rc)
         return rc;
+    const TableMem &t = c->arena[other];
     const int grid = (int)std::min<u64>((c->tcap + 255) / 256, (u64)c->sm_count * 8);
     rehash_kernel<<<grid, 256, 0, c->stream>>>(c->d_tkey, c->d_tmeta, c->tcap, t.key, t.meta, new_cap, &c->d_st->err);
     table_swap_kernel<<<1, 1, 0, c->stream>>>(c->d_st, t.key, t.meta, new_cap, t.cflag);
     c->launches += 2;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
-    table_free(c);
-    table_adopt(c, t, new_cap);
+    table_adopt(c, other, new_cap);
     c->stats.table_rehashes++;
+    return 0;
+}
+
+static int check_state(bpe_cuda_ctx *c)
+{
+    if (getenv("BPE_CUDA_DEBUG"))
+        fprintf(stderr, "[bpe_cuda r%d] merges=%llu n=%llu n_global=%llu D=%lld occ=%llu cap=%llu stop=%u pause=%u static=%u err=%u a=%u b=%u f=%u mult=%u\n",
+                c->rank, c->h_st->merges_done, c->h_st->n, c->h_st->n_global, c->h_st->distinct, c->h_st->occupied, c->h_st->tcap,
+                c->h_st->stop, c->h_st->pause, c->h_st->static_mode, c->h_st->err, c->h_st->a, c->h_st->b, c->h_st->freq,
+                c->h_st->sel_mult),
+        fprintf(stderr, "            layout=%u nr=%u pending=%u cand_T=%u ncand=%u\n", c->h_st->layout, c->h_st->nr, c->h_st->pending,
+                c->h_st->cand_T, c->h_st->ncand);
+    if (c->h_st->err)
+    {
+        set_error("device reported error flags 0x%x (1=table full 2=missing key 4=negative count 8=probe/logic)", c->h_st->err);
+        return BPE_CUDA_ERR_STATE;
+    }
     return 0;
 }
 
 static int poll_state(bpe_cuda_ctx *c)
 {
+    c->h_st = c->h_buf[0];
     CU(cudaMemcpyAsync(c->h_st, c->d_st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (getenv("BPE_CUDA_DEBUG"))
-        fprintf(stderr, "[bpe_cuda r%d] merges=%llu n=%llu n_global=%llu D=%lld occ=%llu cap=%llu stop=%u pause=%u static=%u err=%u a=%u b=%u f=%u mult=%u\n",
-                c->rank, c->h_st->merges_done, c->h_st->n, c->h_st->n_global, c->h_st->distinct, c->h_st->occupied, c->h_st->tcap,
-                c->h_st->stop, c->h_st->pause, c->h_st->static_mode, c->h_st->err, c->h_st->a, c->h_st->b, c->h_st->freq,
-                c->h_st->sel_mult);
-    if (c->h_st->err)
-    {
-        set_error("device reported error flags 0x%x (1=table full 2=missing key 4=negative count)", c->h_st->err);
-        return BPE_CUDA_ERR_STATE;
-    }
-    return 0;
+    return check_state(c);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -481,6 +522,7 @@ static int rebuild_candidates(bpe_cuda_ctx *c, u32 T)
 // long as the table) and overflowing lists fall back to whole-table selection.
 static int choose_candidates(bpe_cuda_ctx *c, u32 best)
 {
+    HostTimer ht(&c->host_ms[1]);
     int rc;
     if (best >= 8)
     {
@@ -506,11 +548,11 @@ static int choose_candidates(bpe_cuda_ctx *c, u32 best)
 static int enqueue_select(bpe_cuda_ctx *c, bool encode)
 {
     if (encode)
-        apply_select_kernel<<<1, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_delta_red, c->d_delta, 1);
+        apply_select_kernel<<<2, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_delta_red, c->d_delta, 1);
     else if (c->cand_T == 0)
         select_kernel<<<c->sel_grid, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_part, c->d_delta_red);
     else
-        apply_select_kernel<<<1, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_delta_red, c->d_delta, 0);
+        apply_select_kernel<<<2, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_delta_red, c->d_delta, 0);
     c->launches++;
     return 0;
 }
@@ -565,8 +607,8 @@ static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool c
     }
     if (encode || c->cand_T)
     {
-        const int agrid = (int)std::min<u64>((4ull * (z + 1) + SEL_THREADS - 1) / SEL_THREADS, (u64)c->sm_count);
-        apply_select_kernel<<<agrid, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_delta_red, c->d_delta, encode ? 1 : 0);
+        const int agrid = (int)std::min<u64>((4ull * (z + 1) + SEL_THREADS - 1) / SEL_THREADS, (u64)c->sm_count * 2);
+        apply_select_kernel<<<agrid + 1, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_delta_red, c->d_delta, encode ? 1 : 0);
         c->launches++;
         prof_mark(c, PT_APPLY);
     }
@@ -582,6 +624,64 @@ static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool c
     return 0;
 }
 
+// ---- the host side of the loop -------------------------------------------------------------------
+// The host never takes part in a merge step; it enqueues steps in batches and looks at the control
+// block once per batch.  To keep the GPU fed while the host looks (or is descheduled), the NEXT batch
+// is enqueued before the poll of the current one is waited for: it is planned on the assumption
+// that the current batch runs to its end, and if that batch stops or pauses instead, every kernel of
+// the speculative batch falls through (they all test the control block first).
+struct BatchPlan
+{
+    u64 m1 = 0;     // merges_done the batch starts from
+    u64 z0 = 0;     // id created by its first pass
+    u64 G = 0;      // steps
+    u64 n_upper = 0;
+    u64 margin = 0; // table slots it may claim
+    bool pending = false, census = false, ranged = false;
+};
+
+static u64 batch_margin(u64 G, u64 z0) { return G * 2 * (z0 + G + 1); }
+
+static u64 batch_steps_for(bpe_cuda_ctx *c, const DevState *h, bool encode, u64 m1, u64 z0)
+{
+    u64 G = (u64)std::max(1, c->batch_steps);
+    if (!encode && h->max_merges != ~0ull)
+        G = (h->max_merges + 1 > m1) ? std::min<u64>(G, h->max_merges - m1 + 1) : 0;
+    if (encode)
+        G = (h->enc_total + 1 > m1) ? std::min<u64>(G, h->enc_total - m1 + 1) : 0;
+    while (G > 4 && batch_margin(G, z0) > c->tcap / 4)
+        G /= 2;
+    return G;
+}
+
+static int enqueue_batch(bpe_cuda_ctx *c, const BatchPlan &p, bool encode)
+{
+    HostTimer ht(&c->host_ms[4]);
+    int rc;
+    if (!p.pending && (rc = enqueue_select(c, encode)))
+        return rc;
+    for (u64 g = 0; g < p.G; g++)
+        if ((rc = enqueue_step(c, (u32)(p.z0 + g), p.n_upper, encode, p.census, p.ranged)))
+            return rc;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int poll_async(bpe_cuda_ctx *c, int slot)
+{
+    CU(cudaMemcpyAsync(c->h_buf[slot], c->d_st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(c->poll_ev[slot], c->stream));
+    return 0;
+}
+
+static int poll_wait(bpe_cuda_ctx *c, int slot)
+{
+    HostTimer ht(&c->host_ms[3]);
+    CU(cudaEventSynchronize(c->poll_ev[slot]));
+    c->h_st = c->h_buf[slot];
+    return check_state(c);
+}
+
 // Same-bucket ties / exact-threshold iterations / layout changes / candidate rebuilds.
 static int resolve_pause(bpe_cuda_ctx *c, bool encode);
 
@@ -593,6 +693,7 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
         return rc;
     for (;;)
     {
+        // ---- the queue is drained and c->h_st is current
         DevState *h = c->h_st;
         if (h->stop == STOP_DONE)
             break;
@@ -604,8 +705,7 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
                 return rc;
             continue;
         }
-        const u64 m0 = h->merges_done;
-        if (!encode && m0 == 0 && !h->pending)
+        if (!encode && h->merges_done == 0 && !h->pending)
         {
             // the very first selection (whole table): its count sizes the candidate list
             if ((rc = ensure_logs(c, 2)))
@@ -619,83 +719,122 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
                 return rc;
             if (c->h_st->merges_done == 0)
                 continue; // stopped or paused before committing anything
+            h = c->h_st;
         }
-        h = c->h_st;
-        const u64 m1 = h->merges_done;
-        const u64 z0 = 256 + m1 - (h->pending ? 1 : 0); // id created by the first pass of this batch
-        // batch size: bounded by the table headroom it may consume (<= 2*(V+1) new keys a step)
-        u64 G = (u64)std::max(1, c->batch_steps);
-        if (!encode && h->max_merges != ~0ull && h->max_merges >= m1)
-            G = std::min<u64>(G, h->max_merges - m1 + 1);
-        if (encode)
-            G = std::min<u64>(G, h->enc_total - m1 + 1);
-        while (G > 4 && G * 2 * (z0 + G + 1) > c->tcap / 4)
-            G /= 2;
-        const u64 margin = G * 2 * (z0 + G + 1);
-        if (h->occupied + margin > c->tcap / 2 + c->tcap / 8)
+        BatchPlan X;
+        X.m1 = h->merges_done;
+        X.pending = h->pending != 0;
+        X.z0 = 256 + X.m1 - (X.pending ? 1 : 0);
+        X.G = batch_steps_for(c, h, encode, X.m1, X.z0);
+        X.margin = batch_margin(X.G, X.z0);
+        X.n_upper = h->n;
+        // table growth: bounded by the headroom two batches may consume (<= 2*(V+1) new keys a step)
+        if (h->occupied + 2 * X.margin > c->tcap / 2 + c->tcap / 8)
         {
             u64 want = 1ull << 20;
-            while (want < 3 * ((u64)h->distinct + margin))
+            while (want < 3 * ((u64)h->distinct + 2 * X.margin))
                 want *= 2;
             if ((rc = table_rehash(c, want)))
                 return rc;
             if (c->cand_T && (rc = choose_candidates(c, std::max<u32>(h->freq, 2 * c->cand_T))))
                 return rc;
-            h = c->h_st;
+            if ((rc = poll_state(c)))
+                return rc;
+            continue;
         }
-        if ((rc = ensure_delta(c, (size_t)(z0 + G + 2))))
+        const u64 batch = (u64)std::max(1, c->batch_steps);
+        if ((rc = ensure_delta(c, (size_t)(X.z0 + 3 * batch + 4))))
             return rc;
-        if ((rc = ensure_logs(c, (size_t)(m1 + G + 2))))
+        if ((rc = ensure_logs(c, (size_t)(X.m1 + 3 * batch + 4))))
             return rc;
         // candidate list upkeep: try a list when selection runs on the whole table, shrink a bloated one
         if (!encode)
         {
-            if (c->cand_T == 0 && h->freq >= 16 && h->freq < c->list_retry_below)
+            const u32 T0 = c->cand_T;
+            if (T0 == 0 && h->freq >= 16 && h->freq < c->list_retry_below)
                 rc = choose_candidates(c, h->freq);
-            else if (c->cand_T && (h->cand_overflow || h->ncand > CAND_CAP * 3 / 4))
-                rc = choose_candidates(c, std::max<u32>(h->freq, c->cand_T + 1));
+            else if (T0 && (h->cand_overflow || h->ncand > CAND_CAP * 3 / 4))
+                rc = choose_candidates(c, std::max<u32>(h->freq, T0 + 1));
             if (rc)
                 return rc;
             h = c->h_st;
         }
         // Worker-table growth is only possible while some slice can still hold thr(B_t) distinct pairs.
-        bool census = false;
+        const bool stat = h->n < STATIC_LIMIT;
         if (!encode && c->world == 1)
         {
-            const bool stat = h->n < STATIC_LIMIT;
             if (c->force_census)
-                census = true;
+                X.census = true;
             else if (stat)
             {
-                const u64 dmax = (u64)h->distinct + margin;
+                const u64 dmax = (u64)h->distinct + X.margin;
                 for (int t = 0; t < REF_THREADS; t++)
                     if (std::min<u64>(h->n / REF_THREADS + 32, dmax) >= resize_threshold(h->bt[t]))
-                        census = true;
+                        X.census = true;
             }
-            if (census && (rc = ensure_resolver(c, h->n, stat ? REF_THREADS : 1)))
+            if (X.census && (rc = ensure_resolver(c, h->n, stat ? REF_THREADS : 1)))
                 return rc;
         }
         // The streaming kernel works on the RANGED layout; everything that needs positions in one dense
         // array (static regime, census) keeps the stream dense and uses the general kernel.
-        const bool ranged = c->want_ranged && !census && !h->static_mode && h->n > 0;
-        if (ranged && h->layout == LAYOUT_DENSE)
+        X.ranged = c->want_ranged && !X.census && !h->static_mode && h->n > 0;
+        if (X.ranged && h->layout == LAYOUT_DENSE)
         {
             partition_kernel<<<1, RANGE_MAX, 0, c->stream>>>(c->d_st);
             c->launches++;
         }
-        else if (!ranged && h->layout == LAYOUT_RANGED)
+        else if (!X.ranged && h->layout == LAYOUT_RANGED)
         {
             repack_kernel<<<RANGE_MAX, 256, 0, c->stream>>>(c->d_st);
             c->launches++;
         }
-        if (!h->pending && (rc = enqueue_select(c, encode)))
+        if ((rc = enqueue_batch(c, X, encode)))
             return rc;
-        for (u64 g = 0; g < G; g++)
-            if ((rc = enqueue_step(c, (u32)(z0 + g), h->n, encode, census, ranged)))
+        // ---- one batch in flight, its poll pending in slot ps
+        DevState snap = *h; // the state X was planned from (a copy: the pinned buffers are rewritten by the polls)
+        const DevState *prev = &snap;
+        u64 occ_bound = snap.occupied + X.margin;
+        int ps = 0;
+        if ((rc = poll_async(c, ps)))
+            return rc;
+        for (;;)
+        {
+            BatchPlan Y;
+            Y.m1 = X.m1 + X.G;
+            Y.z0 = X.z0 + X.G;
+            Y.pending = true;
+            Y.G = batch_steps_for(c, prev, encode, Y.m1, Y.z0);
+            Y.margin = batch_margin(Y.G, Y.z0);
+            Y.n_upper = X.n_upper;
+            Y.census = false;
+            Y.ranged = X.ranged;
+            const bool spec = c->speculate && Y.G > 0 && !X.census && !stat && !prev->static_mode &&
+                              (encode || prev->n_global >= STATIC_LIMIT) &&
+                              occ_bound + Y.margin <= c->tcap / 2 + c->tcap / 8 &&
+                              HDR_INTS + 4 * (Y.z0 + Y.G + 2) <= c->delta_cap && Y.m1 + Y.G + 2 <= c->merges_cap;
+            if (spec)
+            {
+                if ((rc = enqueue_batch(c, Y, encode)))
+                    return rc;
+                if ((rc = poll_async(c, ps ^ 1)))
+                    return rc;
+            }
+            if ((rc = poll_wait(c, ps)))
                 return rc;
-        CU(cudaGetLastError());
-        if ((rc = poll_state(c)))
-            return rc;
+            if (!spec)
+                break;
+            if (c->h_st->stop != STOP_RUN)
+            {
+                // X stopped or paused: Y fell through; drain it and handle the state it left
+                if ((rc = poll_wait(c, ps ^ 1)))
+                    return rc;
+                break;
+            }
+            snap = *c->h_st;
+            occ_bound = snap.occupied + Y.margin;
+            X = Y;
+            ps ^= 1;
+        }
     }
     if (c->h_st->layout == LAYOUT_RANGED)
     {
@@ -761,6 +900,8 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
     CU(cudaSetDevice(c->device));
     const auto t0 = std::chrono::steady_clock::now();
     memset(&c->stats, 0, sizeof c->stats);
+    for (double &x : c->host_ms)
+        x = 0;
     c->launches = 0;
     c->prof_used = 0;
     const u64 n = c->n_bytes;
@@ -787,13 +928,12 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
         CU(cudaMalloc(&c->d_cand, CAND_CAP * sizeof(u32)));
     }
     c->cand_T = 0;
-    // fresh table
-    table_free(c);
+    // fresh table (in the arena the last run left unused, so a big arena stays available for the rehashes)
     {
-        TableMem t;
-        if ((rc = table_alloc(c, 1ull << 20, &t)))
+        const int arena = c->arena[0].cap <= c->arena[1].cap ? 0 : 1;
+        if ((rc = table_alloc(c, 1ull << 20, arena)))
             return rc;
-        table_adopt(c, t, 1ull << 20);
+        table_adopt(c, arena, 1ull << 20);
     }
     if (c->merges_cap == 0)
     {
@@ -898,6 +1038,14 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
     CU(cudaEventDestroy(ev1));
 
     DevState *h = c->h_st;
+    if (getenv("BPE_CUDA_DEBUG"))
+        fprintf(stderr, "[bpe_cuda] host ms: rehash %.1f | candidates %.1f | pauses %.1f | poll waits %.1f | enqueue %.1f\n", c->host_ms[0],
+                c->host_ms[1], c->host_ms[2], c->host_ms[3], c->host_ms[4]);
+    if (getenv("BPE_CUDA_DEBUG") && h->dbg[6])
+        fprintf(stderr, "[bpe_cuda] apply+select phases, avg ns over %llu launches: apply %.0f | done-atomic %.0f | last-block setup %.0f | "
+                        "candidate scan %.0f | reduce %.0f | decide %.0f\n",
+                h->dbg[6], (double)h->dbg[0] / h->dbg[6], (double)h->dbg[1] / h->dbg[6], (double)h->dbg[2] / h->dbg[6],
+                (double)h->dbg[3] / h->dbg[6], (double)h->dbg[4] / h->dbg[6], (double)h->dbg[5] / h->dbg[6]);
     c->res_n_merges = (size_t)h->merges_done;
     c->res_n_tokens = (size_t)h->n;
     c->stats.n_merges = h->merges_done;
@@ -961,6 +1109,7 @@ __global__ void tier_a_commit_kernel(DevState *st, const int32_t *delta_reduced)
 
 static int resolve_pause(bpe_cuda_ctx *c, bool encode)
 {
+    HostTimer ht(&c->host_ms[2]);
     DevState *h = c->h_st;
     int rc;
     const u32 pause = h->pause;
@@ -1075,7 +1224,10 @@ int bpe_cuda_ctx_create(int device, bpe_cuda_ctx_t **out)
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc(&c->d_st, sizeof(DevState)) != cudaSuccess ||
-        cudaMallocHost(&c->h_st, sizeof(DevState)) != cudaSuccess)
+        cudaMallocHost(&c->h_buf[0], sizeof(DevState)) != cudaSuccess ||
+        cudaMallocHost(&c->h_buf[1], sizeof(DevState)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->poll_ev[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->poll_ev[1], cudaEventDisableTiming) != cudaSuccess)
     {
         set_error("context allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete c;
@@ -1120,7 +1272,12 @@ void bpe_cuda_ctx_destroy(bpe_cuda_ctx_t *c)
     cudaFree(c->d_tok_alloc[0]);
     cudaFree(c->d_tok_alloc[1]);
     cudaFree(c->d_st);
-    cudaFreeHost(c->h_st);
+    for (int i = 0; i < 2; i++)
+    {
+        cudaFreeHost(c->h_buf[i]);
+        if (c->poll_ev[i])
+            cudaEventDestroy(c->poll_ev[i]);
+    }
     cudaFree(c->d_desc);
     cudaFree(c->d_pdesc);
     for (int i = 0; i < 2; i++)
@@ -1291,6 +1448,8 @@ int bpe_cuda_ctx_set_option(bpe_cuda_ctx_t *c, const char *name, long long value
     }
     else if (!strcmp(name, "force_census"))
         c->force_census = (int)value;
+    else if (!strcmp(name, "speculate"))
+        c->speculate = (int)(value != 0);
     else if (!strcmp(name, "use_stream"))
         c->use_stream = (int)(value != 0);
     else

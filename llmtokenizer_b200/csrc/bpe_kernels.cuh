@@ -88,6 +88,8 @@ struct DevState
     u32 *rcnt[2];
     u32 *redge[2];
     u32 rp_done, pad_rp;
+    u64 probe_key, probe_slot; // last pair of the stream and its table slot, looked up while the deltas are applied
+    u64 dbg[8]; // phase timers of the fused apply+select kernel (ns, summed; BPE_CUDA_DEBUG prints them)
     // pair table: open addressing, key = a | b<<32, meta = murmur3 | count<<32
     u64 *tkey;
     u64 *tmeta;
@@ -124,6 +126,12 @@ struct DevState
 
 // ---------------------------------------------------------------------------------------------
 // hash_table.c:8-53 on the 8-byte key {u32 a; u32 b}
+__host__ __device__ __forceinline__ u64 gtime()
+{
+    u64 t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __host__ __device__ __forceinline__ u32 rotl32(u32 x, int r) { return (x << r) | (x >> (32 - r)); }
 
 __host__ __device__ __forceinline__ u32 murmur3_pair(u32 a, u32 b)
@@ -615,7 +623,9 @@ __device__ __forceinline__ void sel_block_reduce(u64 &k, u64 &s, u32 &m, SelPart
 // Above 1,048,576 tokens the canonical schedule gives every chunk to worker 0: its
 // table sees all D keys, and its last insert call creates a key iff the stream's last pair occurs
 // exactly once.  That keeps the worker's persistent bucket count exact without touching the stream.
-__device__ inline void dynamic_regime_census(DevState *st, const u32 *rec_all)
+// Does the stream's last pair occur exactly once?  (independent of which pair gets merged next, so
+// the fused apply+select kernel asks this while the candidates are still being scanned)
+__device__ inline u64 last_pair_key(const DevState *st, const u32 *rec_all, u32 buf, u32 layout, u64 n)
 {
     u32 x = SENT, y = SENT;
     if (st->world > 1)
@@ -634,22 +644,60 @@ __device__ inline void dynamic_regime_census(DevState *st, const u32 *rec_all)
         x = last2[0];
         y = last2[1];
     }
-    else if (st->n >= 2)
+    else if (n >= 2)
     {
         StreamEnds e;
-        stream_ends(st, st->cur, st->layout, st->n, e);
+        stream_ends(st, buf, layout, n, e);
         x = e.last2[0];
         y = e.last2[1];
     }
     if (x == SENT || y == SENT)
-        return;
+        return EMPTY_KEY;
+    return (u64)x | ((u64)y << 32);
+}
+__device__ inline bool census_probe(const DevState *st, const u32 *rec_all, u32 buf, u32 layout, u64 n)
+{
+    u32 x = SENT, y = SENT;
+    if (st->world > 1)
+    {
+        int got = 0;
+        u32 last2[2] = {SENT, SENT};
+        for (int q = (int)st->world - 1; q >= 0 && got < 2; q--)
+        {
+            const u32 *rc = rec_all + q * REC_INTS;
+            const u64 len = (u64)rc[0] | ((u64)rc[1] << 32);
+            if (len >= 1 && got < 2)
+                last2[1 - got++] = rc[6];
+            if (len >= 2 && got < 2)
+                last2[1 - got++] = rc[5];
+        }
+        x = last2[0];
+        y = last2[1];
+    }
+    else if (n >= 2)
+    {
+        StreamEnds e;
+        stream_ends(st, buf, layout, n, e);
+        x = e.last2[0];
+        y = e.last2[1];
+    }
+    if (x == SENT || y == SENT)
+        return false;
     const u64 s = table_find(st->tkey, st->tcap, (u64)x | ((u64)y << 32), murmur3_pair(x, y));
-    const bool last_new = (s != NO_SLOT) && (*cnt_ptr(st->tmeta, s) == 1u);
-    st->bt[0] = grown_buckets(st->bt[0], (u64)st->distinct, last_new);
+    return (s != NO_SLOT) && (*reinterpret_cast<volatile u32 *>(cnt_ptr(st->tmeta, s)) == 1u);
 }
 
+// what the last block of the fused kernel works out next to the candidate scan
+struct PreDecide
+{
+    u32 valid;    // the two fields below are filled in
+    u32 last_new; // census_probe()
+    u32 edge;     // on_threshold(D)
+};
+
 // record the chosen pair and prepare the pass (single thread)
-__device__ inline void commit_merge(DevState *st, u32 a, u32 b, u32 freq, const u32 *rec_all, bool encode = false)
+__device__ inline void commit_merge(DevState *st, u32 a, u32 b, u32 freq, const u32 *rec_all, bool encode = false,
+                                    const PreDecide *pre = nullptr)
 {
     const u64 k = st->merges_done;
     st->a = a;
@@ -664,7 +712,10 @@ __device__ inline void commit_merge(DevState *st, u32 a, u32 b, u32 freq, const 
     else
         st->n_global = st->n;
     if (!encode && st->n_global >= STATIC_LIMIT)
-        dynamic_regime_census(st, rec_all);
+    {
+        const bool last_new = (pre && pre->valid) ? (pre->last_new != 0) : census_probe(st, rec_all, st->cur, st->layout, st->n);
+        st->bt[0] = grown_buckets(st->bt[0], (u64)st->distinct, last_new);
+    }
     st->n_next = 0; // the ranged streaming kernel accumulates its ranges' new lengths here
     st->pending = 1;
     st->n_hist[k] = st->n_global;
@@ -677,7 +728,7 @@ constexpr int SEL_THREADS = 512;
 
 // The decision once the best packed key (count << 32 | ~bucket), its multiplicity and a slot holding
 // it are known: stop / pause / commit (bpe.c:730-758).  One thread.
-__device__ inline void decide(DevState *st, u64 k, u64 s, u32 m, const int32_t *delta_reduced)
+__device__ inline void decide(DevState *st, u64 k, u64 s, u32 m, const int32_t *delta_reduced, const PreDecide *pre = nullptr)
 {
     const u64 D = (u64)st->distinct;
     st->sel_key = k;
@@ -714,7 +765,7 @@ __device__ inline void decide(DevState *st, u64 k, u64 s, u32 m, const int32_t *
         st->stop = STOP_PAUSE;
         return;
     }
-    const bool tie = (m > 1), edge = on_threshold(D);
+    const bool tie = (m > 1), edge = (pre && pre->valid) ? (pre->edge != 0) : on_threshold(D);
     if (tie || edge)
     {
         if (tie)
@@ -726,7 +777,7 @@ __device__ inline void decide(DevState *st, u64 k, u64 s, u32 m, const int32_t *
         return;
     }
     const u64 key = st->tkey[s];
-    commit_merge(st, (u32)(key & 0xFFFFFFFFull), (u32)(key >> 32), freq, rec_all);
+    commit_merge(st, (u32)(key & 0xFFFFFFFFull), (u32)(key >> 32), freq, rec_all, false, pre);
     if (st->a == st->b && st->want_ranged && !st->static_mode)
     {
         // run-parity pairing needs the general kernel on a dense stream: the host repacks, then resumes
@@ -1208,20 +1259,53 @@ __device__ __forceinline__ void cand_offer(DevState *st, u64 slot, u32 newcount)
         st->cand_overflow = 1;
 }
 
+// D and the slot occupancy are kept in shared memory while a block works and published once per block:
+// thousands of same-address atomics would otherwise queue up in front of the fence that ends the phase.
+__device__ __forceinline__ u64 table_insert_counted(DevState *st, u64 *tkey, u64 *tmeta, u64 cap, u64 key, u32 h, int *s_occ)
+{
+    u64 s = probe_start(h, cap);
+    for (u64 i = 0; i < cap; i++)
+    {
+        u64 k = tkey[s];
+        if (k == EMPTY_KEY)
+        {
+            k = atomicCAS(tkey + s, EMPTY_KEY, key);
+            if (k == EMPTY_KEY)
+            {
+                *hsh_ptr(tmeta, s) = h;
+                atomicAdd(s_occ, 1);
+                return s;
+            }
+        }
+        if (k == key)
+            return s;
+        s = (s + 1) & (cap - 1);
+    }
+    return NO_SLOT;
+}
+
 __device__ inline void apply_deltas(DevState *st, int32_t *delta_in, int32_t *delta_local, u32 gtid, u32 gsize)
 {
+    __shared__ int s_dD, s_occ;
+    if (threadIdx.x == 0)
+    {
+        s_dD = 0;
+        s_occ = 0;
+    }
+    __syncthreads();
     const u32 a = st->a, b = st->b, z = st->z;
     const u32 total = 4 * (z + 1);
-    u64 *tmeta = st->tmeta;
+    u64 *tmeta = st->tmeta, *tkey = st->tkey;
+    const u64 cap = st->tcap;
     if (gtid == gsize - 1)
     {
         // the merged pair is gone (its own thread, so the probe overlaps the others)
-        const u64 s = table_find(st->tkey, st->tcap, (u64)a | ((u64)b << 32), murmur3_pair(a, b));
+        const u64 s = table_find(tkey, cap, (u64)a | ((u64)b << 32), murmur3_pair(a, b));
         if (s != NO_SLOT)
         {
             const u32 old = atomicExch(cnt_ptr(tmeta, s), 0u);
             if (old)
-                atomicAdd(reinterpret_cast<u64 *>(&st->distinct), ~0ull);
+                atomicAdd(&s_dD, -1);
         }
     }
     for (u32 i = gtid; i < total; i += gsize)
@@ -1258,7 +1342,7 @@ __device__ inline void apply_deltas(DevState *st, int32_t *delta_in, int32_t *de
         const u32 h = murmur3_pair(ka, kb);
         if (vec >= 2)
         {
-            const u64 s = table_insert(st, key, h);
+            const u64 s = table_insert_counted(st, tkey, tmeta, cap, key, h, &s_occ);
             if (s == NO_SLOT)
             {
                 atomicOr(&st->err, ERR_TABLE_FULL);
@@ -1266,12 +1350,12 @@ __device__ inline void apply_deltas(DevState *st, int32_t *delta_in, int32_t *de
             }
             const u32 old = atomicAdd(cnt_ptr(tmeta, s), (u32)d);
             if (old == 0)
-                atomicAdd(reinterpret_cast<u64 *>(&st->distinct), 1ull);
+                atomicAdd(&s_dD, 1);
             cand_offer(st, s, old + (u32)d);
         }
         else
         {
-            const u64 s = table_find(st->tkey, st->tcap, key, h);
+            const u64 s = table_find(tkey, cap, key, h);
             if (s == NO_SLOT)
             {
                 atomicOr(&st->err, ERR_MISSING_KEY);
@@ -1281,8 +1365,16 @@ __device__ inline void apply_deltas(DevState *st, int32_t *delta_in, int32_t *de
             if (old < (u32)d)
                 atomicOr(&st->err, ERR_NEGATIVE);
             if (old == (u32)d)
-                atomicAdd(reinterpret_cast<u64 *>(&st->distinct), ~0ull); // -1
+                atomicAdd(&s_dD, -1);
         }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        if (s_dD)
+            atomicAdd(reinterpret_cast<u64 *>(&st->distinct), (u64)(i64)s_dD);
+        if (s_occ)
+            atomicAdd(&st->occupied, (u64)s_occ);
     }
 }
 
@@ -1327,10 +1419,24 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
         return;
     __shared__ SelPart sm[SEL_THREADS / 32];
     __shared__ bool s_last;
+    const u64 t0 = gtime();
     const bool pending = st->pending != 0;
-    if (pending && !st->skip)
-        apply_deltas(st, delta_in, delta_local, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    const u32 nb_apply = gridDim.x - 1; // the last block of the grid only looks up the stream's last pair
+    if (blockIdx.x == nb_apply)
+    {
+        if (threadIdx.x == 0 && !encode)
+        {
+            const bool flip0 = pending && !st->skip;
+            const u64 key = last_pair_key(st, reinterpret_cast<const u32 *>(delta_in), flip0 ? (st->cur ^ 1u) : st->cur,
+                                          flip0 ? st->layout_next : st->layout, flip0 ? st->n_next : st->n);
+            st->probe_key = key;
+            st->probe_slot = (key == EMPTY_KEY) ? NO_SLOT : table_find(st->tkey, st->tcap, key, murmur3_pair((u32)key, (u32)(key >> 32)));
+        }
+    }
+    else if (pending && !st->skip)
+        apply_deltas(st, delta_in, delta_local, blockIdx.x * blockDim.x + threadIdx.x, nb_apply * blockDim.x);
     __syncthreads();
+    const u64 t1 = gtime();
     if (threadIdx.x == 0)
     {
         __threadfence();
@@ -1340,21 +1446,45 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
     if (!s_last)
         return;
     __threadfence();
+    const u64 t2 = gtime();
+    // ---- last block: the table is final.  Side jobs (flip the buffers, census probe, threshold test)
+    // run on three different warps while everybody scans the candidates.
+    __shared__ PreDecide s_pre;
+    const bool flip = pending && !st->skip;
+    const u32 cur0 = st->cur;
+    const u32 nbuf = flip ? (cur0 ^ 1u) : cur0;
+    const u32 nlayout = flip ? st->layout_next : st->layout;
+    const u64 nn = flip ? *reinterpret_cast<volatile u64 *>(&st->n_next) : st->n;
+    const u64 D = (u64) * reinterpret_cast<volatile i64 *>(&st->distinct);
+    __syncthreads();
     if (threadIdx.x == 0)
     {
         st->sel_done = 0;
         if (pending)
             finish_pass(st);
     }
-    __syncthreads();
     if (encode)
     {
         if (threadIdx.x == 0)
             decide_rank(st, delta_in);
         return;
     }
-    const volatile u64 *meta = st->tmeta;
-    const u64 D = (u64) * reinterpret_cast<volatile i64 *>(&st->distinct);
+    if (threadIdx.x == 32)
+    {
+        // the key and (unless this very apply created it) its slot were looked up while the deltas were applied
+        const u64 key = *reinterpret_cast<volatile u64 *>(&st->probe_key);
+        u64 slot = *reinterpret_cast<volatile u64 *>(&st->probe_slot);
+        if (key != EMPTY_KEY && slot == NO_SLOT)
+            slot = table_find(st->tkey, st->tcap, key, murmur3_pair((u32)key, (u32)(key >> 32)));
+        s_pre.last_new = (key != EMPTY_KEY && slot != NO_SLOT && __ldcg(cnt_ptr(st->tmeta, slot)) == 1u) ? 1u : 0u;
+    }
+    if (threadIdx.x == 64)
+    {
+        s_pre.edge = on_threshold(D) ? 1u : 0u;
+        s_pre.valid = 1;
+    }
+    const u64 t3 = gtime();
+    const u64 *meta = st->tmeta;
     const u64 B = merged_buckets(D);
     const u32 bmask = (u32)(B - 1);
     const u32 ncr = *reinterpret_cast<volatile u32 *>(&st->ncand);
@@ -1362,19 +1492,43 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
     const u32 *cand = st->cand;
     u64 k = 0, s = NO_SLOT;
     u32 m = 0;
-    for (u32 i = threadIdx.x; i < nc; i += SEL_THREADS)
+    constexpr int UNR = 8; // independent gathers in flight per thread
+    for (u32 base = 0; base < nc; base += SEL_THREADS * UNR)
     {
-        const u64 slot = *reinterpret_cast<const volatile u32 *>(cand + i);
-        const u64 mv = meta[slot];
-        if (mv >> 32)
+        u32 sl[UNR];
+        u64 mv[UNR];
+#pragma unroll
+        for (int j = 0; j < UNR; j++)
         {
-            const u64 kk = (mv & 0xFFFFFFFF00000000ull) | (u64)(0xFFFFFFFFu - ((u32)mv & bmask));
-            sel_combine(k, s, m, kk, slot, 1u);
+            const u32 i = base + j * SEL_THREADS + threadIdx.x;
+            sl[j] = (i < nc) ? __ldcg(cand + i) : 0xFFFFFFFFu;
         }
+#pragma unroll
+        for (int j = 0; j < UNR; j++)
+            mv[j] = (sl[j] != 0xFFFFFFFFu) ? __ldcg(meta + sl[j]) : 0ull;
+#pragma unroll
+        for (int j = 0; j < UNR; j++)
+            if (mv[j] >> 32)
+            {
+                const u64 kk = (mv[j] & 0xFFFFFFFF00000000ull) | (u64)(0xFFFFFFFFu - ((u32)mv[j] & bmask));
+                sel_combine(k, s, m, kk, (u64)sl[j], 1u);
+            }
     }
-    sel_block_reduce(k, s, m, sm);
+    const u64 t4 = gtime();
+    sel_block_reduce(k, s, m, sm); // (its barriers also publish s_pre)
     if (threadIdx.x == 0)
-        decide(st, k, s, m, delta_in);
+    {
+        const u64 t5 = gtime();
+        decide(st, k, s, m, delta_in, &s_pre);
+        const u64 t6 = gtime();
+        st->dbg[0] += t1 - t0;
+        st->dbg[1] += t2 - t1;
+        st->dbg[2] += t3 - t2;
+        st->dbg[3] += t4 - t3;
+        st->dbg[4] += t5 - t4;
+        st->dbg[5] += t6 - t5;
+        st->dbg[6] += 1;
+    }
 }
 
 __global__ void cand_reset_kernel(DevState *st)
