@@ -149,6 +149,7 @@ struct bpe_cuda_ctx
     u32 *d_cand = nullptr;   // candidate slots of the argmax (fixed capacity)
     SelPart *d_part = nullptr;
     u32 cand_T = 0;          // host copy of the list threshold we asked for (0 = whole-table selection)
+    int ranges_opt = 0;      // test knob: number of ranges (0 = two per SM)
     int want_ranged = 0;     // this run uses the streaming kernel (RANGED layout) for its a != b passes
     u32 list_retry_below = ~0u; // whole-table mode: try a list again once the best count is below this
     // logs
@@ -760,7 +761,9 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
             h = c->h_st;
         }
         // Worker-table growth is only possible while some slice can still hold thr(B_t) distinct pairs.
-        const bool stat = h->n < STATIC_LIMIT;
+        // (every rank must take the same decisions about what it enqueues - the collectives have to
+        // match - so anything that steers the batch structure looks at replicated state only)
+        const bool stat = (c->world > 1 ? h->n_global : h->n) < STATIC_LIMIT;
         if (!encode && c->world == 1)
         {
             if (c->force_census)
@@ -920,7 +923,7 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
             CU(cudaMalloc(&c->d_rcnt[i], RANGE_MAX * sizeof(u32)));
             CU(cudaMalloc(&c->d_redge[i], RANGE_MAX * EDGE_WORDS * sizeof(u32)));
         }
-    c->rmax = std::min(RANGE_MAX, c->sm_count * c->stream_occ[0]);
+    c->rmax = c->ranges_opt > 0 ? std::min(RANGE_MAX, c->ranges_opt) : std::min(RANGE_MAX, c->sm_count * c->stream_occ[0]);
     c->sel_grid = c->sm_count * 2;
     if (!c->d_part)
     {
@@ -1253,6 +1256,10 @@ int bpe_cuda_ctx_create(int device, bpe_cuda_ctx_t **out)
     }
     if (const char *e = getenv("BPE_CUDA_USE_STREAM"))
         c->use_stream = atoi(e) != 0;
+    if (const char *e = getenv("BPE_CUDA_RANGES"))
+        c->ranges_opt = atoi(e);
+    if (const char *e = getenv("BPE_CUDA_SPECULATE"))
+        c->speculate = atoi(e) != 0;
     *out = c;
     return 0;
 }
@@ -1448,6 +1455,8 @@ int bpe_cuda_ctx_set_option(bpe_cuda_ctx_t *c, const char *name, long long value
     }
     else if (!strcmp(name, "force_census"))
         c->force_census = (int)value;
+    else if (!strcmp(name, "ranges"))
+        c->ranges_opt = (int)value;
     else if (!strcmp(name, "speculate"))
         c->speculate = (int)(value != 0);
     else if (!strcmp(name, "use_stream"))

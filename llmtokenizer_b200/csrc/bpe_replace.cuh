@@ -308,9 +308,11 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
             const u32 valid = (n - base < (u32)V_TILE) ? (n - base) : (u32)V_TILE;
             const bool full = (valid == (u32)V_TILE);
             u32 *sin = s_in + s * V_STAGE_WORDS + 4;
-            if (t == 0 || t == ntiles - 1)
+            if (t == 0 || n < base + (u32)V_TILE + 4u)
             {
-                // first / last tile of the range: its halo comes from the neighbouring ranges
+                // The tile's window reaches over an end of the range: those positions come from the
+                // neighbouring ranges.  (Not only the last tile: when the last one holds fewer than
+                // three tokens, the window of the tile in front of it sees past the end as well.)
                 if (warp == 0)
                 {
                     mbar_wait(&s_halo_ready, 0);
@@ -321,11 +323,11 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
                             sin[-2] = s_halo[0];
                             sin[-1] = s_halo[1];
                         }
-                        if (t == ntiles - 1)
+                        for (u32 k = 0; k < 3; k++)
                         {
-                            sin[valid] = s_halo[2];
-                            sin[valid + 1] = s_halo[3];
-                            sin[valid + 2] = s_halo[4];
+                            const u32 local = n + k - base; // n >= base + 1
+                            if (local < (u32)V_TILE + 4u)
+                                sin[local] = s_halo[2 + k];
                         }
                     }
                 }

@@ -87,6 +87,30 @@ def test_medium_corpora_capped(engine, oracle):
     assert_same(engine, oracle, big, cap=120, what="2.4 MB random text / 120 merges")
 
 
+@pytest.mark.parametrize("ranges", [1, 5, 64, 0])
+def test_ranged_stream_boundaries(engine, oracle, ranges):
+    """The streaming kernel keeps the stream as independently compacted ranges; whatever their number
+    and however their lengths fall relative to the 4,096-token tiles, results must not change.  Small
+    alphabets make replacements land on range ends all the time (including ranges whose last tile holds
+    one or two tokens, and a == b merges that force a repack)."""
+    rng = np.random.default_rng(1000 + ranges)
+    cases = [rng.integers(97, 100, 1_300_000, dtype=np.uint8),
+             np.repeat(rng.integers(97, 101, 500_000, dtype=np.uint8), rng.integers(1, 5, 500_000))[:1_200_000],
+             corpus(0, 1_500_000, 31 + ranges)]
+    for i, data in enumerate(cases):
+        rc, om, ot, _ = oracle.train(data, 60, FAST_CF)
+        ctx = engine.Context(0)
+        ctx.set_option("ranges", ranges)
+        ctx.upload(data)
+        ctx.train(60)
+        m, t = ctx.download()
+        assert np.array_equal(m, om) and np.array_equal(t, ot), f"train case {i} ranges {ranges}"
+        st = ctx.encode(om)
+        _, t2 = ctx.download()
+        ctx.close()
+        assert np.array_equal(t2, ot), f"encode case {i} ranges {ranges}: {st}"
+
+
 def test_encode_matches_training_ids_and_oracle(engine, oracle):
     data = corpus(0, 1_500_000, 5)
     m, t, _ = engine.train(data, max_merges=400)
