@@ -9,9 +9,9 @@ One "step" = one complete training run of the workload (widen, count, all merges
   e2e   : the same through the C-ABI calls with HOST buffers: pinned corpus -> H2D, train, merges +
           ids -> D2H, all inside the timed region
 Workloads:
-  c2 : synthetic 100 MB Zipf-word ASCII corpus, 4,096 merges   (default at N=1, BASELINE configs[1])
+  c2 : synthetic 100 MB Zipf-word ASCII corpus, 4,096 merges   (default at every N, BASELINE configs[1])
   c3 : synthetic 1 GB byte-level Zipf corpus, 32,000 merges, sharded over N GPUs with one NCCL
-       all-reduce of the pair-count deltas per merge             (default at N>1, BASELINE configs[2])
+       all-reduce of the pair-count deltas per merge             (--workload c3, BASELINE configs[2])
   c1 : the reference's random_text.txt to exhaustion (parity configuration; L2-resident)
 N>1 is launched by torch.distributed.run (one rank per GPU); torch.distributed is only the bootstrap
 (NCCL id broadcast, barriers, max-over-ranks), the data path is the engine's own NCCL communicator.
@@ -274,11 +274,12 @@ def bench_engine(args, w, rank, world, local):
     k_bytes = sp["replace_bytes"] / world  # algorithmic bytes on this rank ~ global / N
     achieved = k_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     roofline = {
-        "bound": "hbm", "kernel": "replace_kernel (fused replace + prefix-scan compaction + pair-count deltas)",
+        "bound": "hbm", "kernel": "replace_stream_kernel (fused replace + prefix-scan compaction + pair-count deltas; a == b passes: replace_kernel)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
         "traffic": None, "launches": sp["replace_launches"], "avg_launch_us": 1e3 * k_ms / max(1, sp["replace_launches"]),
         "algorithmic_bytes_per_step": sp["replace_bytes"],
         "kernel_share_of_step": k_ms / sp["ms_device"] if sp["ms_device"] else None,
+        "other_kernels_ms": {"apply_select": sp["apply_ms"] + sp["select_ms"], "host_gaps": sp["gap_ms"]},
         "how": "CUDA events around every replace_kernel launch in one extra step of the same workload "
                "(events off in the timed steps); bytes = sum over merges of 4*(n_k + n_{k+1})",
     }
@@ -330,7 +331,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.workload is None:
-        args.workload = os.environ.get("BPE_BENCH_WORKLOAD") or ("c2" if args.gpus == 1 else "c3")
+        # BASELINE.json quotes the metric on configs[1] (c2); every N runs it so that the per-N values are
+        # comparable.  The 1 GB scaling configuration is `--workload c3` (numbers in DESIGN.md / profiles/).
+        args.workload = os.environ.get("BPE_BENCH_WORKLOAD") or "c2"
     w = WORKLOADS[args.workload]
     rank, world, local = dist_setup(args.gpus)
     if args.impl == "reference":

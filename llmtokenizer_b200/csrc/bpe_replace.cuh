@@ -19,15 +19,15 @@
 // repack_kernel turns the stream back into one dense array when something needs that (a == b merges,
 // the exact tie-break kernels, the static regime below 1,048,576 tokens, the final download).
 //
-// Inside a CTA (10 warps) a ring of shared-memory stages holds one 4,096-token tile (32 "iterations"
+// Inside a CTA (22 warps) a ring of shared-memory stages holds one 4,096-token tile (32 "iterations"
 // of 128 tokens) each:
 //   producer (1 warp)   one 1-D bulk copy (TMA: cp.async.bulk + mbarrier complete_tx) per tile;
-//   scanners (4 warps)  8 iterations each: a lane owns one 128-bit chunk (conflict-free LDS.128),
+//   scanners (8 warps)  4 iterations each: a lane owns one 128-bit chunk (conflict-free LDS.128),
 //                       finds the replacements that start on it, counts kept tokens per iteration
 //                       (ballots), emits the pair-count deltas;
 //   offsets (1 warp)    turns the 32 per-iteration counts into output offsets (running sum), resolves
 //                       the range's halos at the start and publishes its edges at the end;
-//   storers (4 warps)   re-read the tile from shared memory and write the kept tokens: an iteration
+//   storers (12 warps)  re-read the tile from shared memory and write the kept tokens: an iteration
 //                       without replacements (the common case once the pair is rarer than ~1 in 1,000
 //                       tokens) goes registers -> global with 128-bit stores realigned by warp
 //                       shuffles; the others compact through a 136-word per-warp staging buffer.
@@ -37,13 +37,19 @@
 namespace bpe
 {
 
-constexpr int V_SCAN_WARPS = 4;
-constexpr int V_STORE_WARPS = 4;
+#ifndef BPE_V_SCAN_WARPS
+#define BPE_V_SCAN_WARPS 8
+#endif
+#ifndef BPE_V_STORE_WARPS
+#define BPE_V_STORE_WARPS 12
+#endif
+constexpr int V_SCAN_WARPS = BPE_V_SCAN_WARPS;
+constexpr int V_STORE_WARPS = BPE_V_STORE_WARPS;
 constexpr int V_ITERS = 32;                        // iterations (128 tokens) per tile
 constexpr int V_TILE = V_ITERS * 128;              // 4,096 tokens = 16 KB
 constexpr int V_THREADS = (V_SCAN_WARPS + V_STORE_WARPS + 2) * 32;
 #ifndef BPE_V_STAGES
-#define BPE_V_STAGES 5
+#define BPE_V_STAGES 4
 #endif
 constexpr int V_STAGES = BPE_V_STAGES;
 constexpr int V_STAGE_WORDS = V_TILE + 8;          // 4 tokens of halo on either side
