@@ -62,6 +62,9 @@ typedef struct
     uint64_t worker_buckets[16]; /* emulated bucket counts of the reference's 16 worker tables      */
     /* only when profiling is enabled: device time of the other step kernels and of host-induced gaps */
     double select_ms, apply_ms, gap_ms;
+    uint64_t replace_passes;   /* passes over the stream (a pass may carry several merges)            */
+    uint64_t batch_merges;     /* merges that rode along in another merge's pass                       */
+    uint64_t batch_passes;     /* passes that carried more than one merge                              */
 } bpe_cuda_stats_t;
 
 #define BPE_CUDA_OK 0

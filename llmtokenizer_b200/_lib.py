@@ -17,7 +17,8 @@ class Stats(C.Structure):
         "n_input", "n_merges", "n_tokens", "ranks_applied", "same_bucket_ties", "threshold_edges", "resolver_runs",
         "census_runs", "table_rehashes", "table_capacity", "final_distinct", "kernel_launches", "replace_launches",
         "replace_bytes")] + [(n, C.c_double) for n in ("replace_ms", "ms_device", "ms_h2d", "ms_d2h", "ms_total")] + [
-        ("worker_buckets", C.c_uint64 * 16)] + [(n, C.c_double) for n in ("select_ms", "apply_ms", "gap_ms")]
+        ("worker_buckets", C.c_uint64 * 16)] + [(n, C.c_double) for n in ("select_ms", "apply_ms", "gap_ms")] + [
+        (n, C.c_uint64) for n in ("replace_passes", "batch_merges", "batch_passes")]
 
     def as_dict(self):
         d = {n: getattr(self, n) for n, _ in self._fields_ if n != "worker_buckets"}

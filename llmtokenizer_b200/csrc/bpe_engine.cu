@@ -147,8 +147,11 @@ struct bpe_cuda_ctx
     int arena_cur = 0;
     double host_ms[6] = {0, 0, 0, 0, 0, 0}; // wall clock of host-side phases (debug): rehash, candidates, pause, poll wait, enqueue, setup
     u32 *d_cand = nullptr;   // candidate slots of the argmax (fixed capacity)
+    u32 *d_touched = nullptr; // delta counters touched by the current pass
     SelPart *d_part = nullptr;
     u32 cand_T = 0;          // host copy of the list threshold we asked for (0 = whole-table selection)
+    int batch_max = BATCH_MAX; // merges per pass (1 = off)
+    bool run_encode = false;   // the current run applies a given merge list
     int ranges_opt = 0;      // test knob: number of ranges (0 = two per SM)
     int want_ranged = 0;     // this run uses the streaming kernel (RANGED layout) for its a != b passes
     u32 list_retry_below = ~0u; // whole-table mode: try a list again once the best count is below this
@@ -193,6 +196,7 @@ struct bpe_cuda_ctx
 };
 
 static inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+static inline size_t eff_batch(const bpe_cuda_ctx *c) { return (c->world == 1 && !c->run_encode) ? (size_t)std::max(1, std::min(c->batch_max, (int)BATCH_MAX)) : 1; }
 
 struct HostTimer
 {
@@ -247,9 +251,14 @@ static int ensure_stream_buffers(bpe_cuda_ctx *c, size_t n)
     return 0;
 }
 
+// merges that may share one pass in this run (decides how far the device can run ahead of the host's id estimate)
+static inline size_t eff_batch(const bpe_cuda_ctx *c);
+// words of the delta buffer when ids up to z_ub exist: one block of 4 vectors per merge of a batch
+static inline size_t delta_need(const bpe_cuda_ctx *c, size_t z_ub) { return HDR_INTS + eff_batch(c) * 4 * (z_ub + eff_batch(c) + 1); }
+
 static int ensure_delta(bpe_cuda_ctx *c, size_t vocab)
 {
-    const size_t need = HDR_INTS + 4 * (vocab + 1);
+    const size_t need = delta_need(c, vocab);
     if (need <= c->delta_cap)
         return 0;
     size_t cap = c->delta_cap ? c->delta_cap : (size_t)HDR_INTS + 4 * 8192;
@@ -310,6 +319,7 @@ static int ensure_logs(bpe_cuda_ctx *c, size_t merges)
 }
 
 constexpr u32 CAND_CAP = 65536;
+constexpr u32 TOUCHED_CAP = 1u << 20;
 
 // Pair-table memory comes from two arenas that only ever grow and live as long as the context: a
 // rehash builds the new table in the arena the current one does not use.  (cudaMalloc / cudaFree
@@ -574,11 +584,12 @@ static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool c
     if (ranged)
     {
         // RANGED stream, a != b: one CTA per range, no dependency between CTAs (a == b pauses the loop instead)
-        const size_t vsmem = stream_smem_bytes(hist, z);
+        // the histogram always gets its full budget: the device may be ahead of this id estimate, or batch merges
+        const size_t vsmem = stream_smem_bytes(hist, hist ? (u32)c->smem_hist_max_vocab - 1 : 0);
         if (hist)
-            replace_stream_kernel<true><<<c->rmax, V_THREADS, vsmem, c->stream>>>(c->d_st, c->d_delta);
+            replace_stream_kernel<true><<<c->rmax, V_THREADS, vsmem, c->stream>>>(c->d_st, c->d_delta, (u32)(4 * c->smem_hist_max_vocab));
         else
-            replace_stream_kernel<false><<<c->rmax, V_THREADS, vsmem, c->stream>>>(c->d_st, c->d_delta);
+            replace_stream_kernel<false><<<c->rmax, V_THREADS, vsmem, c->stream>>>(c->d_st, c->d_delta, 0);
     }
     else
     {
@@ -608,7 +619,10 @@ static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool c
     }
     if (encode || c->cand_T)
     {
-        const int agrid = (int)std::min<u64>((4ull * (z + 1) + SEL_THREADS - 1) / SEL_THREADS, (u64)c->sm_count * 2);
+        // one GPU: apply walks the list of touched counters (a few thousand); several: the dense all-reduced vectors
+        // every thread looks at one token's four counters (128 bits) per trip; 32 blocks keep the "last block" wait short
+        // (batches are mostly short: size the grid for two merges, the loop is grid-stride)
+        const int agrid = (int)std::min<u64>((std::min<u64>(eff_batch(c), 2) * 4ull * (z + 1) + SEL_THREADS - 1) / SEL_THREADS, 64);
         apply_select_kernel<<<agrid + 1, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_delta_red, c->d_delta, encode ? 1 : 0);
         c->launches++;
         prof_mark(c, PT_APPLY);
@@ -641,7 +655,13 @@ struct BatchPlan
     bool pending = false, census = false, ranged = false;
 };
 
-static u64 batch_margin(u64 G, u64 z0) { return G * 2 * (z0 + G + 1); }
+// table slots a batch of G steps may claim: every replacement creates at most two new pair instances, and a
+// pass replaces at most bm * freq occurrences (the best count never grows)
+static u64 batch_margin(u64 G, u64 z0, u64 bm, u64 freq)
+{
+    const u64 per_merge = std::min<u64>(2 * (z0 + G * bm + 1), freq ? 2 * freq : ~0ull);
+    return G * bm * per_merge;
+}
 
 static u64 batch_steps_for(bpe_cuda_ctx *c, const DevState *h, bool encode, u64 m1, u64 z0)
 {
@@ -650,7 +670,7 @@ static u64 batch_steps_for(bpe_cuda_ctx *c, const DevState *h, bool encode, u64 
         G = (h->max_merges + 1 > m1) ? std::min<u64>(G, h->max_merges - m1 + 1) : 0;
     if (encode)
         G = (h->enc_total + 1 > m1) ? std::min<u64>(G, h->enc_total - m1 + 1) : 0;
-    while (G > 4 && batch_margin(G, z0) > c->tcap / 4)
+    while (G > 4 && batch_margin(G, z0, eff_batch(c), h->freq) > c->tcap / 4)
         G /= 2;
     return G;
 }
@@ -727,7 +747,8 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
         X.pending = h->pending != 0;
         X.z0 = 256 + X.m1 - (X.pending ? 1 : 0);
         X.G = batch_steps_for(c, h, encode, X.m1, X.z0);
-        X.margin = batch_margin(X.G, X.z0);
+        const u64 bm = eff_batch(c);
+        X.margin = batch_margin(X.G, X.z0, bm, h->freq);
         X.n_upper = h->n;
         // table growth: bounded by the headroom two batches may consume (<= 2*(V+1) new keys a step)
         if (h->occupied + 2 * X.margin > c->tcap / 2 + c->tcap / 8)
@@ -744,10 +765,11 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
             continue;
         }
         const u64 batch = (u64)std::max(1, c->batch_steps);
-        if ((rc = ensure_delta(c, (size_t)(X.z0 + 3 * batch + 4))))
+        if ((rc = ensure_delta(c, (size_t)(X.z0 + 3 * batch * bm + 4))))
             return rc;
-        if ((rc = ensure_logs(c, (size_t)(X.m1 + 3 * batch + 4))))
+        if ((rc = ensure_logs(c, (size_t)(X.m1 + 3 * batch * bm + 4))))
             return rc;
+        u64 z_ub = X.z0 + X.G * bm, m_ub = X.m1 + X.G * bm; // how far the device may have got when X is done
         // candidate list upkeep: try a list when selection runs on the whole table, shrink a bloated one
         if (!encode)
         {
@@ -807,14 +829,14 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
             Y.z0 = X.z0 + X.G;
             Y.pending = true;
             Y.G = batch_steps_for(c, prev, encode, Y.m1, Y.z0);
-            Y.margin = batch_margin(Y.G, Y.z0);
+            Y.margin = batch_margin(Y.G, Y.z0, bm, prev->freq);
             Y.n_upper = X.n_upper;
             Y.census = false;
             Y.ranged = X.ranged;
             const bool spec = c->speculate && Y.G > 0 && !X.census && !stat && !prev->static_mode &&
                               (encode || prev->n_global >= STATIC_LIMIT) &&
                               occ_bound + Y.margin <= c->tcap / 2 + c->tcap / 8 &&
-                              HDR_INTS + 4 * (Y.z0 + Y.G + 2) <= c->delta_cap && Y.m1 + Y.G + 2 <= c->merges_cap;
+                              delta_need(c, z_ub + Y.G * bm + 2) <= c->delta_cap && m_ub + Y.G * bm + 2 <= c->merges_cap;
             if (spec)
             {
                 if ((rc = enqueue_batch(c, Y, encode)))
@@ -836,6 +858,11 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
             snap = *c->h_st;
             occ_bound = snap.occupied + Y.margin;
             X = Y;
+            // the poll tells where the device really is; re-anchor the plan on it
+            X.m1 = snap.merges_done;
+            X.z0 = 256 + X.m1 - (snap.pending ? 1 : 0);
+            z_ub = X.z0 + X.G * bm;
+            m_ub = X.m1 + X.G * bm;
             ps ^= 1;
         }
     }
@@ -865,6 +892,9 @@ static int init_state(bpe_cuda_ctx *c, u64 n_local, u64 max_merges, bool encode,
     s.tkey = c->d_tkey;
     s.tmeta = c->d_tmeta;
     s.tcap = c->tcap;
+    s.touched = c->d_touched;
+    s.touched_cap = TOUCHED_CAP;
+    s.use_touched = 0;
     s.cand = c->d_cand;
     s.cflag = c->d_cflag;
     s.cand_cap = CAND_CAP;
@@ -883,6 +913,11 @@ static int init_state(bpe_cuda_ctx *c, u64 n_local, u64 max_merges, bool encode,
     s.use_stream = (u32)c->use_stream;
     c->want_ranged = c->use_stream && !c->force_census && (u64)c->n_bytes * (u64)c->world >= STATIC_LIMIT;
     s.want_ranged = (u32)c->want_ranged;
+    // merges may share a pass only on one GPU for now (the all-reduce would grow with the batch) and never in encode
+    s.batch_max = (u32)eff_batch(c);
+    s.hist_max = (u32)std::max(0, c->smem_hist_max_vocab);
+    s.hist_words = 4 * s.hist_max;
+    s.nb = 1;
     s.layout = s.layout_next = LAYOUT_DENSE;
     s.rmax = (u32)c->rmax;
     for (int i = 0; i < 2; i++)
@@ -902,6 +937,7 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
     int rc;
     CU(cudaSetDevice(c->device));
     const auto t0 = std::chrono::steady_clock::now();
+    c->run_encode = encode;
     memset(&c->stats, 0, sizeof c->stats);
     for (double &x : c->host_ms)
         x = 0;
@@ -929,6 +965,7 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
     {
         CU(cudaMalloc(&c->d_part, (size_t)c->sel_grid * sizeof(SelPart)));
         CU(cudaMalloc(&c->d_cand, CAND_CAP * sizeof(u32)));
+        CU(cudaMalloc(&c->d_touched, TOUCHED_CAP * sizeof(u32)));
     }
     c->cand_T = 0;
     // fresh table (in the arena the last run left unused, so a big arena stays available for the rehashes)
@@ -1046,9 +1083,10 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
                 c->host_ms[1], c->host_ms[2], c->host_ms[3], c->host_ms[4]);
     if (getenv("BPE_CUDA_DEBUG") && h->dbg[6])
         fprintf(stderr, "[bpe_cuda] apply+select phases, avg ns over %llu launches: apply %.0f | done-atomic %.0f | last-block setup %.0f | "
-                        "candidate scan %.0f | reduce %.0f | decide %.0f\n",
+                        "candidate scan %.0f | reduce %.0f | decide %.0f | batch extension %.0f\n",
                 h->dbg[6], (double)h->dbg[0] / h->dbg[6], (double)h->dbg[1] / h->dbg[6], (double)h->dbg[2] / h->dbg[6],
-                (double)h->dbg[3] / h->dbg[6], (double)h->dbg[4] / h->dbg[6], (double)h->dbg[5] / h->dbg[6]);
+                (double)h->dbg[3] / h->dbg[6], (double)h->dbg[4] / h->dbg[6], (double)h->dbg[5] / h->dbg[6],
+                (double)h->dbg[7] / h->dbg[6]);
     c->res_n_merges = (size_t)h->merges_done;
     c->res_n_tokens = (size_t)h->n;
     c->stats.n_merges = h->merges_done;
@@ -1058,6 +1096,8 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
     c->stats.threshold_edges = h->threshold_edges;
     c->stats.table_capacity = c->tcap;
     c->stats.final_distinct = (u64)h->distinct;
+    c->stats.batch_merges = h->batch_merges;
+    c->stats.batch_passes = h->batch_passes;
     c->stats.kernel_launches = c->launches;
     c->stats.ms_device = ms;
     for (int t = 0; t < REF_THREADS; t++)
@@ -1068,12 +1108,18 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
         std::vector<u64> nh(h->merges_done);
         CU(cudaMemcpy(nh.data(), c->d_nhist, h->merges_done * sizeof(u64), cudaMemcpyDeviceToHost));
         u64 bytes = 0;
+        // one pass per entry that is not marked "rode along in a batch"
+        std::vector<u64> pass_n;
         for (u64 k = 0; k < h->merges_done; k++)
+            if (nh[k] != ~0ull)
+                pass_n.push_back(nh[k]);
+        for (size_t k = 0; k < pass_n.size(); k++)
         {
-            const u64 nk = nh[k], nk1 = (k + 1 < h->merges_done) ? nh[k + 1] : c->stats.n_tokens;
+            const u64 nk = pass_n[k], nk1 = (k + 1 < pass_n.size()) ? pass_n[k + 1] : c->stats.n_tokens;
             if (!encode || nk1 != nk)
                 bytes += 4 * (nk + nk1);
         }
+        c->stats.replace_passes = pass_n.size();
         c->stats.replace_bytes = bytes;
     }
     if (c->profile_replace)
@@ -1256,6 +1302,8 @@ int bpe_cuda_ctx_create(int device, bpe_cuda_ctx_t **out)
     }
     if (const char *e = getenv("BPE_CUDA_USE_STREAM"))
         c->use_stream = atoi(e) != 0;
+    if (const char *e = getenv("BPE_CUDA_BATCH_MAX"))
+        c->batch_max = atoi(e);
     if (const char *e = getenv("BPE_CUDA_RANGES"))
         c->ranges_opt = atoi(e);
     if (const char *e = getenv("BPE_CUDA_SPECULATE"))
@@ -1298,6 +1346,7 @@ void bpe_cuda_ctx_destroy(bpe_cuda_ctx_t *c)
     table_free(c);
     cudaFree(c->d_part);
     cudaFree(c->d_cand);
+    cudaFree(c->d_touched);
     cudaFree(c->d_merges);
     cudaFree(c->d_nhist);
     cudaFree(c->d_enc_merges);
@@ -1455,6 +1504,8 @@ int bpe_cuda_ctx_set_option(bpe_cuda_ctx_t *c, const char *name, long long value
     }
     else if (!strcmp(name, "force_census"))
         c->force_census = (int)value;
+    else if (!strcmp(name, "batch_max"))
+        c->batch_max = (int)value;
     else if (!strcmp(name, "ranges"))
         c->ranges_opt = (int)value;
     else if (!strcmp(name, "speculate"))

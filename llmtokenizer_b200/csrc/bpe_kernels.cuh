@@ -24,6 +24,7 @@ constexpr u64 EMPTY_KEY = ~0ull;
 constexpr u64 NO_SLOT = ~0ull;
 
 constexpr int MAX_RANKS = 8;
+constexpr int BATCH_MAX = 8; // merges per pass
 constexpr int REC_INTS = 8;                    // one edge record
 constexpr int HDR_INTS = MAX_RANKS * REC_INTS; // edge records sit in front of the delta vectors
 
@@ -71,8 +72,13 @@ struct DevState
     u64 n;      // tokens in tok[cur] (this rank's shard)
     u64 n_next; // written by the replace kernel
     u64 n_global;
-    // selected merge
+    // selected merge(s): a pass may carry a BATCH of nb merges (a_i, b_i) -> z + i whose 2*nb tokens are
+    // all different and which are provably the next nb merges of the sequential algorithm
     u32 a, b, z, freq;
+    u32 nb, batch_max;
+    u32 hist_max, hist_words; // ids below hist_max run with a shared-memory delta histogram of hist_words counters
+    u32 ba[8], bb[8];
+    u64 batch_merges, batch_passes; // statistics: merges that rode along in a batch / passes with nb > 1
     u32 skip; // encode: this rank's pair does not occur anywhere -> no pass
     // loop control
     u32 stop, pause, err, static_mode;
@@ -88,6 +94,10 @@ struct DevState
     u32 *rcnt[2];
     u32 *redge[2];
     u32 rp_done, pad_rp;
+    // delta entries that became non-zero in the current pass (single GPU): apply walks this list instead of
+    // scanning 4 * nb * V mostly-zero counters
+    u32 *touched;
+    u32 ntouched, touched_cap, touched_overflow, use_touched;
     u64 probe_key, probe_slot; // last pair of the stream and its table slot, looked up while the deltas are applied
     u64 dbg[8]; // phase timers of the fused apply+select kernel (ns, summed; BPE_CUDA_DEBUG prints them)
     // pair table: open addressing, key = a | b<<32, meta = murmur3 | count<<32
@@ -227,6 +237,9 @@ __host__ __device__ __forceinline__ u64 chain_slot(u32 doublings_to_come, u64 r)
 __device__ __forceinline__ u64 probe_start(u32 h, u64 cap) { return (((u64)h * 0x9E3779B97F4A7C15ull) >> 20) & (cap - 1); }
 __device__ __forceinline__ u32 *cnt_ptr(u64 *meta, u64 slot) { return reinterpret_cast<u32 *>(meta + slot) + 1; }
 __device__ __forceinline__ u32 *hsh_ptr(u64 *meta, u64 slot) { return reinterpret_cast<u32 *>(meta + slot); }
+
+// add to a global delta counter (fire and forget: compiles to RED)
+__device__ __forceinline__ void delta_add(DevState *, int32_t *gdelta, u64 idx, int32_t v) { atomicAdd(&gdelta[idx], v); }
 
 __device__ __forceinline__ u64 table_find(const u64 *tkey, u64 cap, u64 key, u32 h)
 {
@@ -705,6 +718,9 @@ __device__ inline void commit_merge(DevState *st, u32 a, u32 b, u32 freq, const 
     st->z = (u32)(256 + k);
     st->freq = freq;
     st->skip = 0;
+    st->nb = 1;
+    st->ba[0] = a;
+    st->bb[0] = b;
     st->merges[2 * k] = a;
     st->merges[2 * k + 1] = b;
     if (st->world > 1)
@@ -722,6 +738,21 @@ __device__ inline void commit_merge(DevState *st, u32 a, u32 b, u32 freq, const 
     st->merges_done = k + 1;
     st->epoch = st->epoch + 1;
     st->ticket = 0;
+}
+
+// one more merge for the pass that is already committed (single thread)
+__device__ inline void extend_batch(DevState *st, u32 a, u32 b)
+{
+    const u64 k = st->merges_done;
+    const u32 i = st->nb;
+    st->ba[i] = a;
+    st->bb[i] = b;
+    st->nb = i + 1;
+    st->merges[2 * k] = a;
+    st->merges[2 * k + 1] = b;
+    st->n_hist[k] = ~0ull; // rides along: no pass of its own
+    st->merges_done = k + 1;
+    st->batch_merges++;
 }
 
 constexpr int SEL_THREADS = 512;
@@ -1162,13 +1193,13 @@ __global__ void __launch_bounds__(R_THREADS) replace_kernel(DevState *st, u64 *d
                             if (SMEM_HIST)
                                 atomicAdd(&s_hist[x * 4 + 0], 1);
                             else
-                                atomicAdd(&gdelta[(u64)x * 4 + 0], 1);
+                                delta_add(st, gdelta, (u64)x * 4 + 0, 1);
                         }
                         const u32 xn = pm ? z : x;
                         if (SMEM_HIST)
                             atomicAdd(&s_hist[xn * 4 + 2], 1);
                         else
-                            atomicAdd(&gdelta[(u64)xn * 4 + 2], 1);
+                            delta_add(st, gdelta, (u64)xn * 4 + 2, 1);
                     }
                     if (y != SENT && !nm)
                     {
@@ -1177,12 +1208,12 @@ __global__ void __launch_bounds__(R_THREADS) replace_kernel(DevState *st, u64 *d
                             if (SMEM_HIST)
                                 atomicAdd(&s_hist[y * 4 + 1], 1);
                             else
-                                atomicAdd(&gdelta[(u64)y * 4 + 1], 1);
+                                delta_add(st, gdelta, (u64)y * 4 + 1, 1);
                         }
                         if (SMEM_HIST)
                             atomicAdd(&s_hist[y * 4 + 3], 1);
                         else
-                            atomicAdd(&gdelta[(u64)y * 4 + 3], 1);
+                            delta_add(st, gdelta, (u64)y * 4 + 3, 1);
                     }
                 }
         }
@@ -1236,7 +1267,7 @@ __global__ void __launch_bounds__(R_THREADS) replace_kernel(DevState *st, u64 *d
         {
             const int32_t v = s_hist[i];
             if (v)
-                atomicAdd(&gdelta[i], v);
+                delta_add(st, gdelta, i, v);
         }
     }
 }
@@ -1293,13 +1324,18 @@ __device__ inline void apply_deltas(DevState *st, int32_t *delta_in, int32_t *de
         s_occ = 0;
     }
     __syncthreads();
-    const u32 a = st->a, b = st->b, z = st->z;
-    const u32 total = 4 * (z + 1);
+    // delta layout: merge i of the batch owns the block [i * 4 * VS, (i + 1) * 4 * VS), VS = z + nb (one slot per
+    // token id that exists after the pass); inside a block, token t holds {-(t,a_i), -(b_i,t), +(t,z_i), +(z_i,t)}
+    const u32 nb = st->nb, z0 = st->z;
+    const u32 VS = z0 + nb;
+    const u32 total = nb * 4 * VS;
     u64 *tmeta = st->tmeta, *tkey = st->tkey;
     const u64 cap = st->tcap;
-    if (gtid == gsize - 1)
+    if (gtid + nb >= gsize && gtid < gsize)
     {
-        // the merged pair is gone (its own thread, so the probe overlaps the others)
+        // the merged pairs are gone (their own threads, so the probes overlap the others)
+        const u32 i = gsize - 1 - gtid;
+        const u32 a = st->ba[i], b = st->bb[i];
         const u64 s = table_find(tkey, cap, (u64)a | ((u64)b << 32), murmur3_pair(a, b));
         if (s != NO_SLOT)
         {
@@ -1308,15 +1344,18 @@ __device__ inline void apply_deltas(DevState *st, int32_t *delta_in, int32_t *de
                 atomicAdd(&s_dD, -1);
         }
     }
-    for (u32 i = gtid; i < total; i += gsize)
+    for (u32 e = gtid; e < total; e += gsize)
     {
-        const int32_t d = delta_in[HDR_INTS + i];
+      {
+        const int32_t d = delta_in[HDR_INTS + e];
         if (delta_local != delta_in)
-            delta_local[HDR_INTS + i] = 0;
+            delta_local[HDR_INTS + e] = 0;
         if (!d)
             continue;
-        delta_in[HDR_INTS + i] = 0;
-        const u32 t = i >> 2, vec = i & 3u;
+        delta_in[HDR_INTS + e] = 0;
+        const u32 bi = e / (4 * VS), r = e - bi * 4 * VS;
+        const u32 a = st->ba[bi], b = st->bb[bi], z = z0 + bi;
+        const u32 t = r >> 2, vec = r & 3u;
         u32 ka, kb;
         if (vec == 0)
         {
@@ -1367,6 +1406,7 @@ __device__ inline void apply_deltas(DevState *st, int32_t *delta_in, int32_t *de
             if (old == (u32)d)
                 atomicAdd(&s_dD, -1);
         }
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0)
@@ -1388,6 +1428,8 @@ __device__ __forceinline__ void finish_pass(DevState *st)
         st->layout = st->layout_next;
     }
     st->pending = 0;
+    st->ntouched = 0;
+    st->touched_overflow = 0;
 }
 
 // whole-table mode: K4 alone (select_kernel follows)
@@ -1485,6 +1527,7 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
     }
     const u64 t3 = gtime();
     const u64 *meta = st->tmeta;
+    const u64 *tkeys = st->tkey;
     const u64 B = merged_buckets(D);
     const u32 bmask = (u32)(B - 1);
     const u32 ncr = *reinterpret_cast<volatile u32 *>(&st->ncand);
@@ -1493,34 +1536,210 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
     u64 k = 0, s = NO_SLOT;
     u32 m = 0;
     constexpr int UNR = 8; // independent gathers in flight per thread
-    for (u32 base = 0; base < nc; base += SEL_THREADS * UNR)
+    // the first trip's candidates stay in registers: when the whole list fits (it almost always does) the
+    // batch extension below works on them without touching memory again
+    u32 sl[UNR];
+    u64 pk[UNR], kk[UNR]; // pair key (a | b << 32), packed order key (count << 32 | ~bucket), 0 = none / taken
+    const bool fits = nc <= (u32)(SEL_THREADS * UNR);
+#pragma unroll
+    for (int j = 0; j < UNR; j++)
     {
-        u32 sl[UNR];
-        u64 mv[UNR];
+        const u32 i = j * SEL_THREADS + threadIdx.x;
+        sl[j] = (i < nc) ? __ldcg(cand + i) : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int j = 0; j < UNR; j++)
+    {
+        const u64 mv = (sl[j] != 0xFFFFFFFFu) ? __ldcg(meta + sl[j]) : 0ull;
+        pk[j] = (sl[j] != 0xFFFFFFFFu) ? __ldcg(tkeys + sl[j]) : 0ull;
+        kk[j] = (mv >> 32) ? ((mv & 0xFFFFFFFF00000000ull) | (u64)(0xFFFFFFFFu - ((u32)mv & bmask))) : 0ull;
+        if (kk[j])
+            sel_combine(k, s, m, kk[j], (u64)sl[j], 1u);
+    }
+    for (u32 base = SEL_THREADS * UNR; base < nc; base += SEL_THREADS * UNR)
+    {
+        u32 sl2[UNR];
+        u64 mv2[UNR];
 #pragma unroll
         for (int j = 0; j < UNR; j++)
         {
             const u32 i = base + j * SEL_THREADS + threadIdx.x;
-            sl[j] = (i < nc) ? __ldcg(cand + i) : 0xFFFFFFFFu;
+            sl2[j] = (i < nc) ? __ldcg(cand + i) : 0xFFFFFFFFu;
         }
 #pragma unroll
         for (int j = 0; j < UNR; j++)
-            mv[j] = (sl[j] != 0xFFFFFFFFu) ? __ldcg(meta + sl[j]) : 0ull;
+            mv2[j] = (sl2[j] != 0xFFFFFFFFu) ? __ldcg(meta + sl2[j]) : 0ull;
 #pragma unroll
         for (int j = 0; j < UNR; j++)
-            if (mv[j] >> 32)
+            if (mv2[j] >> 32)
             {
-                const u64 kk = (mv[j] & 0xFFFFFFFF00000000ull) | (u64)(0xFFFFFFFFu - ((u32)mv[j] & bmask));
-                sel_combine(k, s, m, kk, (u64)sl[j], 1u);
+                const u64 k2 = (mv2[j] & 0xFFFFFFFF00000000ull) | (u64)(0xFFFFFFFFu - ((u32)mv2[j] & bmask));
+                sel_combine(k, s, m, k2, (u64)sl2[j], 1u);
             }
     }
     const u64 t4 = gtime();
     sel_block_reduce(k, s, m, sm); // (its barriers also publish s_pre)
+    __shared__ u64 s_win;          // slot of the pair chosen last (NO_SLOT: stop extending the batch)
+    u64 t5 = 0, t6 = 0;
     if (threadIdx.x == 0)
     {
-        const u64 t5 = gtime();
+        t5 = gtime();
         decide(st, k, s, m, delta_in, &s_pre);
-        const u64 t6 = gtime();
+        t6 = gtime();
+        // A committed a != b merge on a RANGED stream may take the next merges along in its pass.
+        const bool extend = fits && st->stop == STOP_RUN && st->pending && st->batch_max > 1 && st->cand_T && st->want_ranged &&
+                            !st->static_mode && st->a != st->b && st->z >= st->hist_max && st->merges_done < st->max_merges;
+        s_win = extend ? s : NO_SLOT;
+    }
+    __syncthreads();
+    if (s_win != NO_SLOT)
+    {
+        // Which candidates come next in exact selection order?  Every warp extracts its own eight best (warp
+        // shuffles only, everything is in registers); warp 0 then merges the sixteen sorted lists and accepts a
+        // candidate while it is certain to be the next merge of the sequential algorithm:
+        //   * its two tokens occur in none of the accepted pairs (so its count cannot change, and the pass can
+        //     replace all accepted pairs at once without interaction);
+        //   * it is not involved in a same-bucket tie and is not an a == a pair;
+        //   * its count is strictly above the count of the first candidate that was NOT accepted (every pair
+        //     whose count the accepted merges can change or create ranks at or below that one: new pairs never
+        //     exceed the old pairs they come from);
+        //   * D stays far enough from every table-doubling threshold that the bucket order B(D) and the
+        //     workers' bucket counts cannot change inside the batch.
+        constexpr int NW = SEL_THREADS / 32, TOPK = 8;
+        __shared__ u64 s_wk[NW][TOPK], s_wp[NW][TOPK];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const u64 first = s_win;
+#pragma unroll
+        for (int j = 0; j < UNR; j++)
+            if ((u64)sl[j] == first)
+                kk[j] = 0;
+        for (int r = 0; r < TOPK; r++)
+        {
+            u64 bk = 0, bp = 0;
+            u32 bs = 0xFFFFFFFFu;
+#pragma unroll
+            for (int j = 0; j < UNR; j++)
+                if (kk[j] > bk || (kk[j] == bk && bk && sl[j] < bs))
+                {
+                    bk = kk[j];
+                    bs = sl[j];
+                    bp = pk[j];
+                }
+#pragma unroll
+            for (int o = 16; o; o >>= 1)
+            {
+                const u64 k2 = __shfl_xor_sync(0xFFFFFFFFu, bk, o), p2 = __shfl_xor_sync(0xFFFFFFFFu, bp, o);
+                const u32 s2 = __shfl_xor_sync(0xFFFFFFFFu, bs, o);
+                if (k2 > bk || (k2 == bk && s2 < bs))
+                {
+                    bk = k2;
+                    bs = s2;
+                    bp = p2;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < UNR; j++)
+                if (bk && sl[j] == bs)
+                    kk[j] = 0;
+            if (lane == 0)
+            {
+                s_wk[warp][r] = bk;
+                s_wp[warp][r] = bp;
+            }
+        }
+        __syncthreads();
+        if (warp == 0)
+        {
+            const u64 room = st->max_merges - st->merges_done + 1; // merges the cap still allows, this pass included
+            u32 jcap = (u32)min((u64)min(st->batch_max, (u32)BATCH_MAX), room);
+            // while replacements are frequent their deltas are privatised in shared memory: keep the batch small
+            // enough for that histogram (one block of 4 vectors per merge) until the ids outgrow it
+            // (early on only, where a pass makes hundreds of thousands of replacements; later a batch that does not
+            // fit simply sends its deltas to global memory)
+            if (st->z < st->hist_max && st->z < 1024u)
+                while (jcap > 1 && jcap * 4 * (st->z + jcap) > st->hist_words)
+                    jcap--;
+            // lane i keeps accepted pair i; lane w < NW walks warp w's list
+            u32 my_a = (lane == 0) ? st->a : SENT, my_b = (lane == 0) ? st->b : SENT, my_c = (lane == 0) ? st->freq : 0u;
+            u32 nacc = 1, bound = 0, ptr = 0;
+            bool stop = false;
+            for (u32 r = 1; r <= jcap && !stop; r++)
+            {
+                const u64 hk = (lane < NW && ptr < (u32)TOPK) ? s_wk[lane][ptr] : 0ull;
+                u64 bk = hk;
+                u32 bl = (u32)lane;
+#pragma unroll
+                for (int o = 16; o; o >>= 1)
+                {
+                    const u64 k2 = __shfl_xor_sync(0xFFFFFFFFu, bk, o);
+                    const u32 l2 = __shfl_xor_sync(0xFFFFFFFFu, bl, o);
+                    if (k2 > bk || (k2 == bk && l2 < bl))
+                    {
+                        bk = k2;
+                        bl = l2;
+                    }
+                }
+                if (bk == 0)
+                {
+                    bound = st->cand_T - 1; // the list is exhausted: everything else is below the threshold
+                    break;
+                }
+                // same-bucket tie: another list's head, or the winner list's next entry, has the same packed key
+                const u32 wptr = __shfl_sync(0xFFFFFFFFu, ptr, bl);
+                const u64 nextk = (wptr + 1 < (u32)TOPK) ? s_wk[bl][wptr + 1] : 0ull;
+                const bool tie = __ballot_sync(0xFFFFFFFFu, lane != (int)bl && hk == bk) != 0 || nextk == bk;
+                const u64 pay = s_wp[bl][wptr];
+                const u32 cnt = (u32)(bk >> 32), a = (u32)pay, b = (u32)(pay >> 32);
+                const bool overlap =
+                    __ballot_sync(0xFFFFFFFFu, (u32)lane < nacc && (a == my_a || a == my_b || b == my_a || b == my_b)) != 0;
+                const bool ok = !tie && cnt >= 2 && a != b && !overlap && r < jcap;
+                if (!ok)
+                {
+                    bound = cnt;
+                    break;
+                }
+                if ((u32)lane == nacc)
+                {
+                    my_a = a;
+                    my_b = b;
+                    my_c = cnt;
+                }
+                nacc++;
+                if ((u32)lane == bl)
+                    ptr++;
+                // a list that is used up may hide further candidates of its warp: nothing beyond is certain
+                if (wptr + 1 == (u32)TOPK)
+                {
+                    bound = cnt;
+                    stop = true;
+                }
+            }
+            // strictly above the bound; D may move by at most 4 pair instances per replacement
+            while (nacc > 1 && __shfl_sync(0xFFFFFFFFu, my_c, nacc - 1) <= bound)
+                nacc--;
+            u64 dm = 0;
+            for (u32 i = 0; i < nacc; i++)
+                dm += 4ull * __shfl_sync(0xFFFFFFFFu, my_c, i);
+            for (u64 bsz = 256; nacc > 1 && bsz <= (1ull << 40); bsz *= 2)
+            {
+                const u64 thr = resize_threshold(bsz);
+                if (thr + dm >= D && thr <= D + dm)
+                    nacc = 1;
+                if (thr > D + dm)
+                    break;
+            }
+            for (u32 i = 1; i < nacc; i++)
+            {
+                const u32 a = __shfl_sync(0xFFFFFFFFu, my_a, i), b = __shfl_sync(0xFFFFFFFFu, my_b, i);
+                if (lane == 0)
+                    extend_batch(st, a, b);
+            }
+            if (lane == 0 && nacc > 1)
+                st->batch_passes++;
+        }
+    }
+    if (threadIdx.x == 0)
+    {
         st->dbg[0] += t1 - t0;
         st->dbg[1] += t2 - t1;
         st->dbg[2] += t3 - t2;
@@ -1528,6 +1747,7 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
         st->dbg[4] += t5 - t4;
         st->dbg[5] += t6 - t5;
         st->dbg[6] += 1;
+        st->dbg[7] += gtime() - t6;
     }
 }
 

@@ -163,12 +163,81 @@ __device__ __forceinline__ bool iter_bits(const u32 *sin, int j, int lane, u32 a
 }
 __device__ __forceinline__ u32 keep_mask(u32 bits, u32 v) { return ((1u << v) - 1u) & ~((bits >> 4) | ((bits & 7u) << 1)) & 0xFu; }
 
+// Batched pass (nb > 1 merges at once; all 2*nb tokens differ, so at most one pair can match at a position).
+// 1 + index of the pair that matches (x, y), 0 if none
+__device__ __forceinline__ u32 pair_of(u32 x, u32 y, u32 nb, const u32 *ba, const u32 *bb)
+{
+    u32 r = 0;
+    for (u32 i = 0; i < nb; i++)
+        if (x == ba[i] && y == bb[i])
+            r = i + 1;
+    return r;
+}
+// as iter_bits; mi = four nibbles, 1 + index of the pair whose replacement starts on token k.  The pairs are read
+// from shared memory (broadcast loads: registers are scarce at 22 warps per CTA); a thread first asks whether any of
+// its four tokens is the first token of ANY pair (one compare per token and pair) and only then looks for the pair.
+__device__ __forceinline__ bool iter_bits_multi(const u32 *sin, int j, int lane, u32 nb, const u32 *ra, const u32 *rb, u32 valid,
+                                                bool full, const uint4 &c, u32 &bits, u32 &v, u32 &mi)
+{
+    const u32 nxl = sin[(j + 1) * 128];
+    const u32 pvl = sin[j * 128 - 1];
+    u32 nx = __shfl_down_sync(0xFFFFFFFFu, c.x, 1);
+    if (lane == 31)
+        nx = nxl;
+    const u32 x0 = __shfl_sync(0xFFFFFFFFu, c.x, 0);
+    bool hit = false, carry_hit = false;
+#pragma unroll 1
+    for (u32 i = 0; i < nb; i++)
+    {
+        const u32 a = ra[i];
+        hit = hit || c.x == a || c.y == a || c.z == a || c.w == a;
+        carry_hit = carry_hit || (pvl == a && x0 == rb[i]);
+    }
+    mi = 0;
+    if (hit)
+    {
+#pragma unroll 1
+        for (u32 i = 0; i < nb; i++)
+            {
+                const u32 a = ra[i], b = rb[i];
+                if (c.x == a && c.y == b)
+                    mi |= (i + 1);
+                if (c.y == a && c.z == b)
+                    mi |= (i + 1) << 4;
+                if (c.z == a && c.w == b)
+                    mi |= (i + 1) << 8;
+                if (c.w == a && nx == b)
+                    mi |= (i + 1) << 12;
+            }
+    }
+    const u32 carry = carry_hit ? 1u : 0u;
+    v = 4;
+    if (!full)
+    {
+        const u32 p = (u32)j * 128u + (u32)lane * 4u;
+        v = (p >= valid) ? 0u : ((valid - p < 4u) ? (valid - p) : 4u);
+        mi &= (v >= 4) ? 0xFFFFu : ((1u << (4 * v)) - 1u);
+    }
+    bits = 0;
+    if (!(__any_sync(0xFFFFFFFFu, mi != 0) || carry || !full))
+        return false;
+    const bool m3 = (mi >> 12) != 0;
+    const u32 mb3 = __ballot_sync(0xFFFFFFFFu, m3);
+    const u32 r0 = (((mb3 << 1) | carry) >> lane) & 1u;
+    bits = ((mi & 0xFu) ? 1u : 0u) | ((mi & 0xF0u) ? 2u : 0u) | ((mi & 0xF00u) ? 4u : 0u) | ((mi & 0xF000u) ? 8u : 0u) | (r0 << 4);
+    return true;
+}
+
 template <bool SMEM_HIST>
-__global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *st, int32_t *delta)
+__global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *st, int32_t *delta, u32 hist_words)
 {
     if (st->stop != STOP_RUN || st->skip)
         return;
-    const u32 a = st->a, b = st->b, z = st->z;
+    const u32 a = st->a, b = st->b, z = st->z, nb = st->nb;
+    const u32 VS = z + nb; // delta block stride, see apply_deltas
+    // the host gave the shared-memory delta histogram hist_words counters: enough for this (batch of) merge(s)?
+    const u32 hist_need = nb * 4 * VS;
+    const bool use_hist = SMEM_HIST && hist_need <= hist_words;
     const u32 cta = blockIdx.x, nr = st->nr;
     if (a == b || st->layout != LAYOUT_RANGED)
     {
@@ -191,6 +260,7 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
     __shared__ __align__(8) u64 s_full[V_STAGES], s_scanned[V_STAGES], s_ready[V_STAGES], s_empty[V_STAGES], s_halo_ready;
     __shared__ StageMeta s_meta[V_STAGES];
     __shared__ u32 s_halo[5]; // tokens at range positions -2, -1, n, n+1, n+2
+    __shared__ u32 s_ba[BATCH_MAX], s_bb[BATCH_MAX];
 
     const u32 *__restrict__ in = st->tok[ibuf] + (u64)cta * rcap;
     u32 *__restrict__ out = st->tok[obuf] + (u64)cta * rcap;
@@ -212,9 +282,14 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (SMEM_HIST)
-        for (u32 i = tid; i < 4 * (z + 1); i += V_THREADS)
+    if (use_hist)
+        for (u32 i = tid; i < hist_need; i += V_THREADS)
             s_hist[i] = 0;
+    if (tid < BATCH_MAX)
+    {
+        s_ba[tid] = (tid < (int)nb) ? st->ba[tid] : SENT;
+        s_bb[tid] = (tid < (int)nb) ? st->bb[tid] : SENT;
+    }
     __syncthreads();
 
     if (warp == V_WARP_PRODUCER)
@@ -345,8 +420,10 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
             {
                 const int j = warp * PER + jj;
                 const uint4 c = *reinterpret_cast<const uint4 *>(sin + j * 128 + lane * 4);
-                u32 bits, v, ktj = 128;
-                if (iter_bits(sin, j, lane, a, b, valid, full, c, bits, v))
+                u32 bits, v, mi = 0, ktj = 128;
+                const bool slow_it = (nb == 1) ? iter_bits(sin, j, lane, a, b, valid, full, c, bits, v)
+                                               : iter_bits_multi(sin, j, lane, nb, s_ba, s_bb, valid, full, c, bits, v, mi);
+                if (slow_it)
                 {
                     slow |= 1u << j;
                     ktj = __reduce_add_sync(0xFFFFFFFFu, (u32)__popc(keep_mask(bits, v)));
@@ -360,33 +437,71 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
                             {
                                 const int p = p0 + k;
                                 const u32 xl = sin[p - 1], yr = sin[p + 2];
-                                const bool pm = (sin[p - 2] == a) && (xl == b); // a replacement ends right in front
-                                const bool nm = (yr == a) && (sin[p + 3] == b); // another one starts right behind
-                                if (xl != SENT)
+                                if (nb == 1)
                                 {
-                                    const u32 xn = pm ? z : xl;
-                                    if (SMEM_HIST)
+                                    const bool pm = (sin[p - 2] == a) && (xl == b); // a replacement ends right in front
+                                    const bool nm = (yr == a) && (sin[p + 3] == b); // another one starts right behind
+                                    if (xl != SENT)
                                     {
-                                        atomicAdd(&s_hist[xl * 4 + 0], 1);
-                                        atomicAdd(&s_hist[xn * 4 + 2], 1);
+                                        const u32 xn = pm ? z : xl;
+                                        if (use_hist)
+                                        {
+                                            atomicAdd(&s_hist[xl * 4 + 0], 1);
+                                            atomicAdd(&s_hist[xn * 4 + 2], 1);
+                                        }
+                                        else
+                                        {
+                                            delta_add(st, gdelta, (u64)xl * 4 + 0, 1);
+                                            delta_add(st, gdelta, (u64)xn * 4 + 2, 1);
+                                        }
                                     }
-                                    else
+                                    if (yr != SENT && !nm)
                                     {
-                                        atomicAdd(&gdelta[(u64)xl * 4 + 0], 1);
-                                        atomicAdd(&gdelta[(u64)xn * 4 + 2], 1);
+                                        if (use_hist)
+                                        {
+                                            atomicAdd(&s_hist[yr * 4 + 1], 1);
+                                            atomicAdd(&s_hist[yr * 4 + 3], 1);
+                                        }
+                                        else
+                                        {
+                                            delta_add(st, gdelta, (u64)yr * 4 + 1, 1);
+                                            delta_add(st, gdelta, (u64)yr * 4 + 3, 1);
+                                        }
                                     }
                                 }
-                                if (yr != SENT && !nm)
+                                else
                                 {
-                                    if (SMEM_HIST)
+                                    // batched: the same ownership rule, with "a replacement" meaning one of any pair
+                                    const u32 i = ((mi >> (4 * k)) & 15u) - 1u;
+                                    const u32 pm = pair_of(sin[p - 2], xl, nb, s_ba, s_bb);
+                                    const bool nm = pair_of(yr, sin[p + 3], nb, s_ba, s_bb) != 0;
+                                    const u64 off = (u64)i * 4 * VS;
+                                    if (xl != SENT)
                                     {
-                                        atomicAdd(&s_hist[yr * 4 + 1], 1);
-                                        atomicAdd(&s_hist[yr * 4 + 3], 1);
+                                        const u32 xn = pm ? (z + pm - 1u) : xl;
+                                        if (use_hist)
+                                        {
+                                            atomicAdd(&s_hist[off + xl * 4 + 0], 1);
+                                            atomicAdd(&s_hist[off + xn * 4 + 2], 1);
+                                        }
+                                        else
+                                        {
+                                            delta_add(st, gdelta, off + (u64)xl * 4 + 0, 1);
+                                            delta_add(st, gdelta, off + (u64)xn * 4 + 2, 1);
+                                        }
                                     }
-                                    else
+                                    if (yr != SENT && !nm)
                                     {
-                                        atomicAdd(&gdelta[(u64)yr * 4 + 1], 1);
-                                        atomicAdd(&gdelta[(u64)yr * 4 + 3], 1);
+                                        if (use_hist)
+                                        {
+                                            atomicAdd(&s_hist[off + yr * 4 + 1], 1);
+                                            atomicAdd(&s_hist[off + yr * 4 + 3], 1);
+                                        }
+                                        else
+                                        {
+                                            delta_add(st, gdelta, off + (u64)yr * 4 + 1, 1);
+                                            delta_add(st, gdelta, off + (u64)yr * 4 + 3, 1);
+                                        }
                                     }
                                 }
                             }
@@ -475,8 +590,11 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
                 else
                 {
                     // compaction through the per-warp staging buffer
-                    u32 bits, v;
-                    iter_bits(sin, j, lane, a, b, valid, full, c, bits, v);
+                    u32 bits, v, mi = 0x1111u; // single merge: every replacement is pair 0
+                    if (nb == 1)
+                        iter_bits(sin, j, lane, a, b, valid, full, c, bits, v);
+                    else
+                        iter_bits_multi(sin, j, lane, nb, s_ba, s_bb, valid, full, c, bits, v, mi);
                     const u32 keep = keep_mask(bits, v);
                     const u32 kc = (u32)__popc(keep);
                     u32 incl = kc;
@@ -494,7 +612,7 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
 #pragma unroll
                     for (int k = 0; k < 4; k++)
                         if ((keep >> k) & 1u)
-                            stg[rk++] = ((bits >> k) & 1u) ? z : tk[k];
+                            stg[rk++] = ((bits >> k) & 1u) ? (z + ((mi >> (4 * k)) & 15u) - 1u) : tk[k];
                     __syncwarp();
                     // stg[ph + i] <-> out[g + i], i in [0, ktj): aligned 16 B chunks line up on both sides
                     u32 *ob = out + (g - ph); // 16 B aligned
@@ -521,14 +639,14 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
         }
     }
 
-    if (SMEM_HIST)
+    if (use_hist)
     {
         __syncthreads();
-        for (u32 i = tid; i < 4 * (z + 1); i += V_THREADS)
+        for (u32 i = tid; i < hist_need; i += V_THREADS)
         {
             const int32_t v = s_hist[i];
             if (v)
-                atomicAdd(&gdelta[i], v);
+                delta_add(st, gdelta, i, v);
         }
     }
 }

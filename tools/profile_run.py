@@ -47,7 +47,7 @@ def main():
     st = None
     for i in range(args.repeat):
         st = ctx.train(args.merges)
-        print(f"run {i}: ms_device {st['ms_device']:.2f} ms_total {st['ms_total']:.2f} replace_ms {st['replace_ms']:.2f} select_ms {st['select_ms']:.2f} apply_ms {st['apply_ms']:.2f} gap_ms {st['gap_ms']:.2f}", file=sys.stderr)
+        print(f"run {i}: ms_device {st['ms_device']:.2f} ms_total {st['ms_total']:.2f} replace_ms {st['replace_ms']:.2f} select_ms {st['select_ms']:.2f} apply_ms {st['apply_ms']:.2f} gap_ms {st['gap_ms']:.2f} passes {st['replace_passes']} batched {st['batch_merges']}", file=sys.stderr)
     out = {"train": {k: st[k] for k in ("n_input", "n_merges", "n_tokens", "kernel_launches", "replace_launches",
                                         "replace_bytes", "replace_ms", "ms_device", "table_capacity", "final_distinct")}}
     if st["replace_ms"] > 0:
