@@ -145,12 +145,17 @@ struct bpe_cuda_ctx
         u64 cap = 0;
     } arena[2];
     int arena_cur = 0;
+    int l2_pin = 0;               // keep the pair table in L2 (access policy window); measured: no gain for apply/select and
+                                  // 25 % slower passes on B200, so off (BPE_CUDA_L2_PIN=1 turns it on)
+    size_t l2_window_max = 0, l2_persist_bytes = 0;
     double host_ms[6] = {0, 0, 0, 0, 0, 0}; // wall clock of host-side phases (debug): rehash, candidates, pause, poll wait, enqueue, setup
     u32 *d_cand = nullptr;   // candidate slots of the argmax (fixed capacity)
     u32 *d_touched = nullptr; // delta counters touched by the current pass
     SelPart *d_part = nullptr;
     u32 cand_T = 0;          // host copy of the list threshold we asked for (0 = whole-table selection)
     int batch_max = BATCH_MAX; // merges per pass (1 = off)
+    int batch_min_z = -1;      // (-1: where the shared-memory delta histogram ends)
+    int pad_unused_bz = 0;       // first id from which merges may share a pass
     bool run_encode = false;   // the current run applies a given merge list
     int ranges_opt = 0;      // test knob: number of ranges (0 = two per SM)
     int want_ranged = 0;     // this run uses the streaming kernel (RANGED layout) for its a != b passes
@@ -331,19 +336,35 @@ static int table_alloc(bpe_cuda_ctx *c, u64 cap, int arena)
     TableMem &t = c->arena[arena];
     if (t.cap < cap)
     {
-        cudaFree(t.key);
-        cudaFree(t.meta);
-        cudaFree(t.cflag);
+        cudaFree(t.key); // one allocation: keys, then meta, then the candidate bits
         t = TableMem();
-        CU(cudaMalloc(&t.key, cap * sizeof(u64)));
-        CU(cudaMalloc(&t.meta, cap * sizeof(u64)));
-        CU(cudaMalloc(&t.cflag, cap / 8));
+        CU(cudaMalloc(&t.key, cap * 2 * sizeof(u64) + cap / 8));
         t.cap = cap;
     }
+    // (the sub-arrays are placed for the capacity in use, so that the live table is one contiguous window)
+    t.meta = t.key + cap;
+    t.cflag = reinterpret_cast<u32 *>(t.meta + cap);
     CU(cudaMemsetAsync(t.key, 0xFF, cap * sizeof(u64), c->stream));
-    CU(cudaMemsetAsync(t.meta, 0, cap * sizeof(u64), c->stream));
-    CU(cudaMemsetAsync(t.cflag, 0, cap / 8, c->stream));
+    CU(cudaMemsetAsync(t.meta, 0, cap * sizeof(u64) + cap / 8, c->stream));
     return 0;
+}
+
+// Ask for the live table (keys + counts) to be kept in L2 across the streaming passes: the apply / select
+// kernels are chains of dependent accesses to it, and every pass would otherwise evict it.
+static void table_pin_l2(bpe_cuda_ctx *c, int arena, u64 cap)
+{
+    if (!c->l2_pin || c->l2_window_max == 0)
+        return;
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof v);
+    const size_t bytes = std::min<size_t>((size_t)cap * 2 * sizeof(u64), (size_t)c->l2_window_max);
+    v.accessPolicyWindow.base_ptr = c->arena[arena].key;
+    v.accessPolicyWindow.num_bytes = bytes;
+    v.accessPolicyWindow.hitRatio = std::min(1.0f, (float)((double)c->l2_persist_bytes / (double)bytes));
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess)
+        cudaGetLastError(); // a hint only
 }
 
 static void table_free(bpe_cuda_ctx *c)
@@ -351,8 +372,6 @@ static void table_free(bpe_cuda_ctx *c)
     for (int i = 0; i < 2; i++)
     {
         cudaFree(c->arena[i].key);
-        cudaFree(c->arena[i].meta);
-        cudaFree(c->arena[i].cflag);
         c->arena[i] = TableMem();
     }
     c->d_tkey = c->d_tmeta = nullptr;
@@ -366,6 +385,7 @@ static void table_adopt(bpe_cuda_ctx *c, int arena, u64 cap)
     c->d_tmeta = c->arena[arena].meta;
     c->d_cflag = c->arena[arena].cflag;
     c->tcap = cap;
+    table_pin_l2(c, arena, cap);
 }
 
 static int table_rehash(bpe_cuda_ctx *c, u64 new_cap)
@@ -917,6 +937,7 @@ static int init_state(bpe_cuda_ctx *c, u64 n_local, u64 max_merges, bool encode,
     s.batch_max = (u32)eff_batch(c);
     s.hist_max = (u32)std::max(0, c->smem_hist_max_vocab);
     s.hist_words = 4 * s.hist_max;
+    s.batch_min_z = c->batch_min_z >= 0 ? (u32)c->batch_min_z : s.hist_max;
     s.nb = 1;
     s.layout = s.layout_next = LAYOUT_DENSE;
     s.rmax = (u32)c->rmax;
@@ -1271,6 +1292,21 @@ int bpe_cuda_ctx_create(int device, bpe_cuda_ctx_t **out)
     bpe_cuda_ctx *c = new bpe_cuda_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    if (const char *e = getenv("BPE_CUDA_L2_PIN"))
+        c->l2_pin = atoi(e);
+    if (c->l2_pin && prop.persistingL2CacheMaxSize > 0)
+    {
+        c->l2_persist_bytes = (size_t)prop.persistingL2CacheMaxSize;
+        c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->l2_persist_bytes) != cudaSuccess)
+        {
+            cudaGetLastError();
+            c->l2_window_max = 0;
+        }
+        if (getenv("BPE_CUDA_DEBUG"))
+            fprintf(stderr, "[bpe_cuda] L2 %d MB, persisting max %zu MB, window max %zu MB\n", prop.l2CacheSize >> 20,
+                    c->l2_persist_bytes >> 20, c->l2_window_max >> 20);
+    }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc(&c->d_st, sizeof(DevState)) != cudaSuccess ||
         cudaMallocHost(&c->h_buf[0], sizeof(DevState)) != cudaSuccess ||
@@ -1504,6 +1540,8 @@ int bpe_cuda_ctx_set_option(bpe_cuda_ctx_t *c, const char *name, long long value
     }
     else if (!strcmp(name, "force_census"))
         c->force_census = (int)value;
+    else if (!strcmp(name, "batch_min_z"))
+        c->batch_min_z = (int)value;
     else if (!strcmp(name, "batch_max"))
         c->batch_max = (int)value;
     else if (!strcmp(name, "ranges"))

@@ -76,6 +76,7 @@ struct DevState
     // all different and which are provably the next nb merges of the sequential algorithm
     u32 a, b, z, freq;
     u32 nb, batch_max;
+    u32 batch_min_z, pad_bz;  // no batching below this id (test / tuning knob)
     u32 hist_max, hist_words; // ids below hist_max run with a shared-memory delta histogram of hist_words counters
     u32 ba[8], bb[8];
     u64 batch_merges, batch_passes; // statistics: merges that rode along in a batch / passes with nb > 1
@@ -1588,13 +1589,13 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
         t6 = gtime();
         // A committed a != b merge on a RANGED stream may take the next merges along in its pass.
         const bool extend = fits && st->stop == STOP_RUN && st->pending && st->batch_max > 1 && st->cand_T && st->want_ranged &&
-                            !st->static_mode && st->a != st->b && st->z >= st->hist_max && st->merges_done < st->max_merges;
+                            !st->static_mode && st->a != st->b && st->z >= st->batch_min_z && st->merges_done < st->max_merges;
         s_win = extend ? s : NO_SLOT;
     }
     __syncthreads();
     if (s_win != NO_SLOT)
     {
-        // Which candidates come next in exact selection order?  Every warp extracts its own eight best (warp
+        // Which candidates come next in exact selection order?  Every warp extracts its own four best (warp
         // shuffles only, everything is in registers); warp 0 then merges the sixteen sorted lists and accepts a
         // candidate while it is certain to be the next merge of the sequential algorithm:
         //   * its two tokens occur in none of the accepted pairs (so its count cannot change, and the pass can
@@ -1605,7 +1606,7 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
         //     exceed the old pairs they come from);
         //   * D stays far enough from every table-doubling threshold that the bucket order B(D) and the
         //     workers' bucket counts cannot change inside the batch.
-        constexpr int NW = SEL_THREADS / 32, TOPK = 8;
+        constexpr int NW = SEL_THREADS / 32, TOPK = 4;
         __shared__ u64 s_wk[NW][TOPK], s_wp[NW][TOPK];
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const u64 first = s_win;
@@ -1654,9 +1655,8 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
             u32 jcap = (u32)min((u64)min(st->batch_max, (u32)BATCH_MAX), room);
             // while replacements are frequent their deltas are privatised in shared memory: keep the batch small
             // enough for that histogram (one block of 4 vectors per merge) until the ids outgrow it
-            // (early on only, where a pass makes hundreds of thousands of replacements; later a batch that does not
-            // fit simply sends its deltas to global memory)
-            if (st->z < st->hist_max && st->z < 1024u)
+            // (beyond hist_max ids a pass makes few enough replacements for global atomics)
+            if (st->z < st->hist_max)
                 while (jcap > 1 && jcap * 4 * (st->z + jcap) > st->hist_words)
                     jcap--;
             // lane i keeps accepted pair i; lane w < NW walks warp w's list
@@ -1717,10 +1717,15 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
             // strictly above the bound; D may move by at most 4 pair instances per replacement
             while (nacc > 1 && __shfl_sync(0xFFFFFFFFu, my_c, nacc - 1) <= bound)
                 nacc--;
+            // How far can D move inside the batch?  A merge changes at most four pair instances per replacement,
+            // and at most one key per delta counter (four per token id).
             u64 dm = 0;
+            const u64 per_tok = 4ull * (st->z + BATCH_MAX + 1);
             for (u32 i = 0; i < nacc; i++)
-                dm += 4ull * __shfl_sync(0xFFFFFFFFu, my_c, i);
-            for (u64 bsz = 256; nacc > 1 && bsz <= (1ull << 40); bsz *= 2)
+                dm += min(4ull * __shfl_sync(0xFFFFFFFFu, my_c, i), per_tok);
+            // the merged table is rebuilt from 65,536 buckets every iteration: no doubling threshold may lie
+            // within reach on either side; the worker table only ever grows: its next threshold must be out of reach
+            for (u64 bsz = 65536; nacc > 1 && bsz <= (1ull << 40); bsz *= 2)
             {
                 const u64 thr = resize_threshold(bsz);
                 if (thr + dm >= D && thr <= D + dm)
@@ -1728,6 +1733,8 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
                 if (thr > D + dm)
                     break;
             }
+            if (nacc > 1 && D + dm >= resize_threshold(st->bt[0]))
+                nacc = 1;
             for (u32 i = 1; i < nacc; i++)
             {
                 const u32 a = __shfl_sync(0xFFFFFFFFu, my_a, i), b = __shfl_sync(0xFFFFFFFFu, my_b, i);

@@ -51,7 +51,9 @@ constexpr int V_THREADS = (V_SCAN_WARPS + V_STORE_WARPS + 2) * 32;
 #ifndef BPE_V_STAGES
 #define BPE_V_STAGES 4
 #endif
-constexpr int V_STAGES = BPE_V_STAGES;
+constexpr int V_STAGES = BPE_V_STAGES;   // ring depth without the shared-memory delta histogram
+constexpr int V_STAGES_HIST = 4;         // with it (a 3-deep ring + a 40 KB histogram so that early merges could share passes
+                                         // was tried: slower - those passes are bound by their replacements, not by streaming)
 constexpr int V_STAGE_WORDS = V_TILE + 8;          // 4 tokens of halo on either side
 constexpr int V_STAGING_WORDS = 136;               // per storer warp: 128 tokens + alignment phase
 constexpr u32 V_TILE_BYTES = V_STAGE_WORDS * 4;
@@ -60,7 +62,8 @@ constexpr int V_WARP_OFFSETS = V_WARP_PRODUCER + 1;
 
 __host__ __device__ inline size_t stream_smem_bytes(bool hist, u32 z)
 {
-    return (size_t)V_STAGES * V_TILE_BYTES + (size_t)V_STORE_WARPS * V_STAGING_WORDS * 4 + (hist ? 16 * ((size_t)z + 1) : 0);
+    return (size_t)(hist ? V_STAGES_HIST : V_STAGES) * V_TILE_BYTES + (size_t)V_STORE_WARPS * V_STAGING_WORDS * 4 +
+           (hist ? 16 * ((size_t)z + 1) : 0);
 }
 
 // ---- mbarrier / bulk-copy wrappers (PTX ISA: mbarrier, cp.async.bulk) --------------------------
@@ -231,6 +234,7 @@ __device__ __forceinline__ bool iter_bits_multi(const u32 *sin, int j, int lane,
 template <bool SMEM_HIST>
 __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *st, int32_t *delta, u32 hist_words)
 {
+    constexpr int NST = SMEM_HIST ? V_STAGES_HIST : V_STAGES;
     if (st->stop != STOP_RUN || st->skip)
         return;
     const u32 a = st->a, b = st->b, z = st->z, nb = st->nb;
@@ -254,11 +258,11 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
         st->layout_next = LAYOUT_RANGED;
 
     extern __shared__ __align__(16) u32 smem[];
-    u32 *s_in = smem;                                       // V_STAGES x V_STAGE_WORDS
-    u32 *s_staging = smem + V_STAGES * V_STAGE_WORDS;       // V_STORE_WARPS x V_STAGING_WORDS
+    u32 *s_in = smem;                                       // NST x V_STAGE_WORDS
+    u32 *s_staging = smem + NST * V_STAGE_WORDS;       // V_STORE_WARPS x V_STAGING_WORDS
     int32_t *s_hist = reinterpret_cast<int32_t *>(s_staging + V_STORE_WARPS * V_STAGING_WORDS);
-    __shared__ __align__(8) u64 s_full[V_STAGES], s_scanned[V_STAGES], s_ready[V_STAGES], s_empty[V_STAGES], s_halo_ready;
-    __shared__ StageMeta s_meta[V_STAGES];
+    __shared__ __align__(8) u64 s_full[NST], s_scanned[NST], s_ready[NST], s_empty[NST], s_halo_ready;
+    __shared__ StageMeta s_meta[NST];
     __shared__ u32 s_halo[5]; // tokens at range positions -2, -1, n, n+1, n+2
     __shared__ u32 s_ba[BATCH_MAX], s_bb[BATCH_MAX];
 
@@ -270,7 +274,7 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
 
     if (tid == 0)
     {
-        for (int s = 0; s < V_STAGES; s++)
+        for (int s = 0; s < NST; s++)
         {
             mbar_init(&s_full[s], 1);
             mbar_init(&s_scanned[s], V_SCAN_WARPS);
@@ -299,9 +303,9 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
         {
             for (u32 t = 0; t < ntiles; t++)
             {
-                const u32 s = t % V_STAGES;
-                if (t >= V_STAGES)
-                    mbar_wait(&s_empty[s], ((t / V_STAGES) & 1u) ^ 1u);
+                const u32 s = t % NST;
+                if (t >= NST)
+                    mbar_wait(&s_empty[s], ((t / NST) & 1u) ^ 1u);
                 s_meta[s].slowmask = 0; // every storer is done with the previous tile of this stage
                 mbar_arrive_expect_tx(&s_full[s], V_TILE_BYTES);
                 bulk_load(s_in + s * V_STAGE_WORDS, in + (u64)t * V_TILE - 4, V_TILE_BYTES, &s_full[s]);
@@ -339,9 +343,9 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
         u32 run = 0; // kept tokens of the tiles in front, i.e. the output offset inside the range
         for (u32 t = 0; t < ntiles; t++)
         {
-            const u32 s = t % V_STAGES;
+            const u32 s = t % NST;
             StageMeta &sm = s_meta[s];
-            mbar_wait(&s_scanned[s], (t / V_STAGES) & 1u);
+            mbar_wait(&s_scanned[s], (t / NST) & 1u);
             const u32 cnt = sm.cnt[lane];
             u32 incl = cnt;
 #pragma unroll
@@ -361,8 +365,8 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
             run += __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
         // wait for the storers of the last tiles, then publish the range's new length and edges
-        for (u32 t = (ntiles > (u32)V_STAGES ? ntiles - V_STAGES : 0); t < ntiles; t++)
-            mbar_wait(&s_empty[t % V_STAGES], (t / V_STAGES) & 1u);
+        for (u32 t = (ntiles > (u32)NST ? ntiles - NST : 0); t < ntiles; t++)
+            mbar_wait(&s_empty[t % NST], (t / NST) & 1u);
         __threadfence_block();
         if (lane == 0)
         {
@@ -382,9 +386,9 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
         constexpr int PER = V_ITERS / V_SCAN_WARPS;
         for (u32 t = 0; t < ntiles; t++)
         {
-            const u32 s = t % V_STAGES;
+            const u32 s = t % NST;
             StageMeta &sm = s_meta[s];
-            mbar_wait(&s_full[s], (t / V_STAGES) & 1u);
+            mbar_wait(&s_full[s], (t / NST) & 1u);
             const u32 base = t * V_TILE;
             const u32 valid = (n - base < (u32)V_TILE) ? (n - base) : (u32)V_TILE;
             const bool full = (valid == (u32)V_TILE);
@@ -526,9 +530,9 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
         u32 *stg = s_staging + sw * V_STAGING_WORDS;
         for (u32 t = 0; t < ntiles; t++)
         {
-            const u32 s = t % V_STAGES;
+            const u32 s = t % NST;
             StageMeta &sm = s_meta[s];
-            mbar_wait(&s_ready[s], (t / V_STAGES) & 1u);
+            mbar_wait(&s_ready[s], (t / NST) & 1u);
             const u32 base = t * V_TILE;
             const u32 valid = (n - base < (u32)V_TILE) ? (n - base) : (u32)V_TILE;
             const bool full = (valid == (u32)V_TILE);
