@@ -126,6 +126,7 @@ struct StageMeta
     u32 slowmask;        // bit j: iteration j has replacements / removals / invalid tokens
     u32 cnt[V_ITERS];    // kept tokens per iteration
     u32 pre[V_ITERS];    // exclusive prefix of cnt
+    unsigned char bits[V_ITERS][32]; // single-merge passes: what iter_bits found, per lane (scanner -> storer)
 };
 
 // Replacements that start on my chunk and whether my first token is removed, for iteration j of the
@@ -432,13 +433,15 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
                     slow |= 1u << j;
                     ktj = __reduce_add_sync(0xFFFFFFFFu, (u32)__popc(keep_mask(bits, v)));
                     // ---- pair-count deltas of the replacements that start on my tokens
+                    if (nb == 1)
+                        sm.bits[j][lane] = (unsigned char)bits;
                     if (bits & 0xFu)
                     {
                         const int p0 = j * 128 + lane * 4;
-#pragma unroll
-                        for (int k = 0; k < 4; k++)
-                            if ((bits >> k) & 1u)
+                        // one trip per replacement (a lane has at most two), not one per token position
+                        for (u32 todo = bits & 0xFu; todo; todo &= todo - 1u)
                             {
+                                const int k = __ffs(todo) - 1;
                                 const int p = p0 + k;
                                 const u32 xl = sin[p - 1], yr = sin[p + 2];
                                 if (nb == 1)
@@ -514,13 +517,13 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
                 if (lane == 0)
                     sm.cnt[j] = ktj;
             }
+            __syncwarp(); // every lane's sm.bits are written before lane 0 publishes the tile
             if (lane == 0)
             {
                 if (slow)
                     atomicOr(&sm.slowmask, slow);
                 mbar_arrive(&s_scanned[s]);
             }
-            __syncwarp();
         }
     }
     else
@@ -596,20 +599,22 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
                     // compaction through the per-warp staging buffer
                     u32 bits, v, mi = 0x1111u; // single merge: every replacement is pair 0
                     if (nb == 1)
-                        iter_bits(sin, j, lane, a, b, valid, full, c, bits, v);
+                    {
+                        // what the scanner found (the barrier chain scanned -> ready orders the accesses)
+                        bits = sm.bits[j][lane];
+                        const u32 p = (u32)j * 128u + (u32)lane * 4u;
+                        v = full ? 4u : ((p >= valid) ? 0u : ((valid - p < 4u) ? (valid - p) : 4u));
+                    }
                     else
                         iter_bits_multi(sin, j, lane, nb, s_ba, s_bb, valid, full, c, bits, v, mi);
                     const u32 keep = keep_mask(bits, v);
                     const u32 kc = (u32)__popc(keep);
-                    u32 incl = kc;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1)
-                    {
-                        const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                        if (lane >= o)
-                            incl += t;
-                    }
-                    const u32 ktj = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    // exclusive prefix of the kept counts (0..4 each) from three ballots
+                    const u32 lt = (1u << lane) - 1u;
+                    const u32 incl = kc + (u32)__popc(__ballot_sync(0xFFFFFFFFu, kc & 1u) & lt) +
+                                     2u * (u32)__popc(__ballot_sync(0xFFFFFFFFu, kc & 2u) & lt) +
+                                     4u * (u32)__popc(__ballot_sync(0xFFFFFFFFu, kc & 4u) & lt);
+                    const u32 ktj = sm.cnt[j];
                     const u32 ph = g & 3u;
                     u32 rk = ph + incl - kc;
                     const u32 tk[4] = {c.x, c.y, c.z, c.w};
