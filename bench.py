@@ -276,12 +276,15 @@ def bench_engine(args, w, rank, world, local):
     roofline = {
         "bound": "hbm", "kernel": "replace_stream_kernel (fused replace + prefix-scan compaction + pair-count deltas; a == b passes: replace_kernel)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-        "traffic": None, "launches": sp["replace_launches"], "avg_launch_us": 1e3 * k_ms / max(1, sp["replace_launches"]),
+        "traffic": None, "launches": sp["replace_passes"], "avg_launch_us": 1e3 * k_ms / max(1, sp["replace_passes"]),
+        "merges_per_pass": sp["n_merges"] / max(1, sp["replace_passes"]),
         "algorithmic_bytes_per_step": sp["replace_bytes"],
         "kernel_share_of_step": k_ms / sp["ms_device"] if sp["ms_device"] else None,
         "other_kernels_ms": {"apply_select": sp["apply_ms"] + sp["select_ms"], "host_gaps": sp["gap_ms"]},
-        "how": "CUDA events around every replace_kernel launch in one extra step of the same workload "
-               "(events off in the timed steps); bytes = sum over merges of 4*(n_k + n_{k+1})",
+        "how": "CUDA events around every pass (replace_stream_kernel / replace_kernel launch) in one extra step of the same "
+               "workload (events off in the timed steps); bytes = sum over PASSES of 4*(tokens in + tokens out) - a pass "
+               "that carries several provably-next merges is counted once; traffic: see profiles/README.md (ncu: DRAM "
+               "bytes = algorithmic bytes, no re-reads)",
     }
     whole = (sp["replace_bytes"] / world + 9 * shard.size) / (sp["ms_device"] * 1e-3) / 1e9
     roofline["whole_step_gbs"] = whole
@@ -315,7 +318,8 @@ def bench_engine(args, w, rank, world, local):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "engine_stats": {k: sp[k] for k in ("same_bucket_ties", "threshold_edges", "resolver_runs", "census_runs",
-                                                 "table_rehashes", "table_capacity", "final_distinct")},
+                                                 "table_rehashes", "table_capacity", "final_distinct", "replace_passes",
+                                                 "batch_merges", "batch_passes")},
         }
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -19,7 +19,7 @@
 // repack_kernel turns the stream back into one dense array when something needs that (a == b merges,
 // the exact tie-break kernels, the static regime below 1,048,576 tokens, the final download).
 //
-// Inside a CTA (22 warps) a ring of shared-memory stages holds one 4,096-token tile (32 "iterations"
+// Inside a CTA (18 warps) a ring of shared-memory stages holds one 4,096-token tile (32 "iterations"
 // of 128 tokens) each:
 //   producer (1 warp)   one 1-D bulk copy (TMA: cp.async.bulk + mbarrier complete_tx) per tile;
 //   scanners (8 warps)  4 iterations each: a lane owns one 128-bit chunk (conflict-free LDS.128),
@@ -27,7 +27,7 @@
 //                       (ballots), emits the pair-count deltas;
 //   offsets (1 warp)    turns the 32 per-iteration counts into output offsets (running sum), resolves
 //                       the range's halos at the start and publishes its edges at the end;
-//   storers (12 warps)  re-read the tile from shared memory and write the kept tokens: an iteration
+//   storers (8 warps)   re-read the tile from shared memory and write the kept tokens: an iteration
 //                       without replacements (the common case once the pair is rarer than ~1 in 1,000
 //                       tokens) goes registers -> global with 128-bit stores realigned by warp
 //                       shuffles; the others compact through a 136-word per-warp staging buffer.
@@ -41,7 +41,7 @@ namespace bpe
 #define BPE_V_SCAN_WARPS 8
 #endif
 #ifndef BPE_V_STORE_WARPS
-#define BPE_V_STORE_WARPS 12
+#define BPE_V_STORE_WARPS 8
 #endif
 constexpr int V_SCAN_WARPS = BPE_V_SCAN_WARPS;
 constexpr int V_STORE_WARPS = BPE_V_STORE_WARPS;
@@ -91,13 +91,15 @@ __device__ __forceinline__ bool mbar_try_wait(u64 *bar, u32 parity)
 }
 __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
 {
+    // try_wait with a suspend-time hint: the warp sleeps in hardware instead of burning issue slots in a poll
+    // loop (ncu: a third of an early pass's instructions were YIELD / TRYWAIT / BRA of idle roles)
     const u32 addr = smem_addr(bar);
     u32 ok;
     do
     {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok)
-                     : "r"(addr), "r"(parity)
+                     : "r"(addr), "r"(parity), "r"(2000u)
                      : "memory");
     } while (!ok);
 }
@@ -178,7 +180,7 @@ __device__ __forceinline__ u32 pair_of(u32 x, u32 y, u32 nb, const u32 *ba, cons
     return r;
 }
 // as iter_bits; mi = four nibbles, 1 + index of the pair whose replacement starts on token k.  The pairs are read
-// from shared memory (broadcast loads: registers are scarce at 22 warps per CTA); a thread first asks whether any of
+// from shared memory (broadcast loads; registers are better spent elsewhere); a thread first asks whether any of
 // its four tokens is the first token of ANY pair (one compare per token and pair) and only then looks for the pair.
 __device__ __forceinline__ bool iter_bits_multi(const u32 *sin, int j, int lane, u32 nb, const u32 *ra, const u32 *rb, u32 valid,
                                                 bool full, const uint4 &c, u32 &bits, u32 &v, u32 &mi)
@@ -513,6 +515,9 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
                                 }
                             }
                     }
+                    // the delta loop is lane-divergent: reconverge here, or every shuffle / ballot of the next
+                    // iteration runs through the slow divergent-warp path (measured: a third of all instructions)
+                    __syncwarp();
                 }
                 if (lane == 0)
                     sm.cnt[j] = ktj;
