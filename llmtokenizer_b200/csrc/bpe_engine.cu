@@ -157,6 +157,7 @@ struct bpe_cuda_ctx
     int batch_min_z = -1;      // (-1: where the shared-memory delta histogram ends)
     int pad_unused_bz = 0;       // first id from which merges may share a pass
     bool run_encode = false;   // the current run applies a given merge list
+    u64 run_max_merges = 0;    // its merge cap (0 = none)
     int ranges_opt = 0;      // test knob: number of ranges (0 = two per SM)
     int want_ranged = 0;     // this run uses the streaming kernel (RANGED layout) for its a != b passes
     u32 list_retry_below = ~0u; // whole-table mode: try a list again once the best count is below this
@@ -201,7 +202,18 @@ struct bpe_cuda_ctx
 };
 
 static inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
-static inline size_t eff_batch(const bpe_cuda_ctx *c) { return (c->world == 1 && !c->run_encode) ? (size_t)std::max(1, std::min(c->batch_max, (int)BATCH_MAX)) : 1; }
+// One GPU: up to BATCH_MAX.  Several GPUs: the all-reduce carries one block of delta vectors per merge of a batch,
+// so batches are used (and kept to 4) only while the vocabulary is small (decided once per run from the merge cap,
+// identically on every rank).
+static inline size_t eff_batch(const bpe_cuda_ctx *c)
+{
+    if (c->run_encode)
+        return 1;
+    const int bm = std::max(1, std::min(c->batch_max, (int)BATCH_MAX));
+    if (c->world == 1)
+        return (size_t)bm;
+    return (c->run_max_merges != 0 && c->run_max_merges <= 8192 - 256) ? (size_t)std::min(bm, 4) : 1;
+}
 
 struct HostTimer
 {
@@ -590,8 +602,10 @@ static int enqueue_select(bpe_cuda_ctx *c, bool encode)
 
 // One merge step for the committed merge that creates id z: [census] -> replace (+scan+deltas) ->
 // [edge record, ncclAllReduce] -> apply deltas + select the next merge.
-static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool census, bool ranged)
+static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool census, bool ranged, u64 z_ub = 0)
 {
+    if (z_ub < z)
+        z_ub = z;
     prof_mark(c, PT_GAP);
     if (census)
     {
@@ -634,8 +648,9 @@ static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool c
     {
         edge_record_kernel<<<1, 32, 0, c->stream>>>(c->d_st, c->d_delta, 1);
         c->launches++;
-        NC(g_nccl.AllReduce(c->d_delta, c->d_delta_red, HDR_INTS + 4 * ((size_t)z + 1), ncclInt32, ncclSum, c->comm,
-                            c->stream));
+        // (the device may be ahead of the host's id estimate when merges share passes: reduce up to the bound)
+        const size_t words = std::min(delta_need(c, (size_t)z_ub), c->delta_cap);
+        NC(g_nccl.AllReduce(c->d_delta, c->d_delta_red, words, ncclInt32, ncclSum, c->comm, c->stream));
     }
     if (encode || c->cand_T)
     {
@@ -672,6 +687,7 @@ struct BatchPlan
     u64 G = 0;      // steps
     u64 n_upper = 0;
     u64 margin = 0; // table slots it may claim
+    u64 zub0 = 0;   // upper bound of the id created by its first pass (the device may be ahead of z0)
     bool pending = false, census = false, ranged = false;
 };
 
@@ -702,7 +718,7 @@ static int enqueue_batch(bpe_cuda_ctx *c, const BatchPlan &p, bool encode)
     if (!p.pending && (rc = enqueue_select(c, encode)))
         return rc;
     for (u64 g = 0; g < p.G; g++)
-        if ((rc = enqueue_step(c, (u32)(p.z0 + g), p.n_upper, encode, p.census, p.ranged)))
+        if ((rc = enqueue_step(c, (u32)(p.z0 + g), p.n_upper, encode, p.census, p.ranged, p.zub0 + (g + 1) * eff_batch(c))))
             return rc;
     CU(cudaGetLastError());
     return 0;
@@ -766,6 +782,7 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
         X.m1 = h->merges_done;
         X.pending = h->pending != 0;
         X.z0 = 256 + X.m1 - (X.pending ? 1 : 0);
+        X.zub0 = X.z0;
         X.G = batch_steps_for(c, h, encode, X.m1, X.z0);
         const u64 bm = eff_batch(c);
         X.margin = batch_margin(X.G, X.z0, bm, h->freq);
@@ -847,6 +864,7 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
             BatchPlan Y;
             Y.m1 = X.m1 + X.G;
             Y.z0 = X.z0 + X.G;
+            Y.zub0 = z_ub;
             Y.pending = true;
             Y.G = batch_steps_for(c, prev, encode, Y.m1, Y.z0);
             Y.margin = batch_margin(Y.G, Y.z0, bm, prev->freq);
@@ -881,6 +899,7 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
             // the poll tells where the device really is; re-anchor the plan on it
             X.m1 = snap.merges_done;
             X.z0 = 256 + X.m1 - (snap.pending ? 1 : 0);
+            X.zub0 = X.z0;
             z_ub = X.z0 + X.G * bm;
             m_ub = X.m1 + X.G * bm;
             ps ^= 1;
@@ -959,6 +978,7 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
     CU(cudaSetDevice(c->device));
     const auto t0 = std::chrono::steady_clock::now();
     c->run_encode = encode;
+    c->run_max_merges = encode ? 0 : max_merges;
     memset(&c->stats, 0, sizeof c->stats);
     for (double &x : c->host_ms)
         x = 0;
@@ -1165,12 +1185,28 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
 
 // ---------------------------------------------------------------------------------------------
 // pause handling
-__global__ void tier_a_commit_kernel(DevState *st, const int32_t *delta_reduced)
+__global__ void tie_reset_kernel(DevState *st) { st->probe_key = ~0ull; }
+__global__ void tie_min_key_kernel(DevState *st)
 {
-    // Provisional: takes the first maximal slot.  Replaced by the exact chain-order resolver.
     if (st->stop != STOP_PAUSE)
         return;
-    const u64 key = st->tkey[st->sel_slot];
+    const u64 cap = st->tcap;
+    const u64 B = merged_buckets((u64)st->distinct);
+    const u32 bmask = (u32)(B - 1);
+    const u64 want = st->sel_key;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x)
+    {
+        const u64 mv = st->tmeta[i];
+        if ((mv >> 32) && ((mv & 0xFFFFFFFF00000000ull) | (u64)(0xFFFFFFFFu - ((u32)mv & bmask))) == want)
+            atomicMin(&st->probe_key, st->tkey[i]);
+    }
+}
+__global__ void tier_a_commit_kernel(DevState *st, const int32_t *delta_reduced)
+{
+    // sharded stream: among the pairs that tie inside the winning bucket, the smallest pair key (same on every rank)
+    if (st->stop != STOP_PAUSE)
+        return;
+    const u64 key = st->probe_key != ~0ull ? st->probe_key : st->tkey[st->sel_slot];
     commit_merge(st, (u32)(key & 0xFFFFFFFFull), (u32)(key >> 32), (u32)(st->sel_key >> 32),
                  reinterpret_cast<const u32 *>(delta_reduced));
     st->stop = STOP_RUN;
@@ -1226,8 +1262,11 @@ static int resolve_pause(bpe_cuda_ctx *c, bool encode)
     if (c->world > 1)
     {
         // sharded stream: chain order is taken from the table order (documented limitation; counted)
+        // (the smallest pair key among the tied pairs: slot numbers differ from rank to rank, pair keys do not)
+        tie_reset_kernel<<<1, 1, 0, c->stream>>>(c->d_st);
+        tie_min_key_kernel<<<(int)std::min<u64>((c->tcap + 255) / 256, (u64)c->sm_count * 8), 256, 0, c->stream>>>(c->d_st);
         tier_a_commit_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_delta_red);
-        c->launches++;
+        c->launches += 3;
         return enqueue_step(c, (u32)(256 + merges_done), n, encode, false, false);
     }
     const u32 slices = (n < STATIC_LIMIT) ? REF_THREADS : 1;
