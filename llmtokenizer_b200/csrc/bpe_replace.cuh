@@ -182,8 +182,8 @@ __device__ __forceinline__ u32 pair_of(u32 x, u32 y, u32 nb, const u32 *ba, cons
 // as iter_bits; mi = four nibbles, 1 + index of the pair whose replacement starts on token k.  The pairs are read
 // from shared memory (broadcast loads; registers are better spent elsewhere); a thread first asks whether any of
 // its four tokens is the first token of ANY pair (one compare per token and pair) and only then looks for the pair.
-__device__ __forceinline__ bool iter_bits_multi(const u32 *sin, int j, int lane, u32 nb, const u32 *ra, const u32 *rb, u32 valid,
-                                                bool full, const uint4 &c, u32 &bits, u32 &v, u32 &mi)
+__device__ __forceinline__ bool iter_bits_multi(const u32 *sin, int j, int lane, u32 nb, const u32 *ra, u32 valid, bool full,
+                                                const uint4 &c, u32 &bits, u32 &v, u32 &mi)
 {
     const u32 nxl = sin[(j + 1) * 128];
     const u32 pvl = sin[j * 128 - 1];
@@ -191,29 +191,41 @@ __device__ __forceinline__ bool iter_bits_multi(const u32 *sin, int j, int lane,
     if (lane == 31)
         nx = nxl;
     const u32 x0 = __shfl_sync(0xFFFFFFFFu, c.x, 0);
+    // two pairs per 128-bit broadcast load: (a0, b0, a1, b1); unused entries hold SENT, which no token equals
+    const uint4 *p4 = reinterpret_cast<const uint4 *>(ra);
     bool hit = false, carry_hit = false;
-#pragma unroll 1
-    for (u32 i = 0; i < nb; i++)
-    {
-        const u32 a = ra[i];
-        hit = hit || c.x == a || c.y == a || c.z == a || c.w == a;
-        carry_hit = carry_hit || (pvl == a && x0 == rb[i]);
-    }
+#pragma unroll
+    for (int q = 0; q < BATCH_MAX / 2; q++)
+        if ((u32)(2 * q) < nb)
+        {
+            const uint4 t = p4[q];
+            hit = hit || c.x == t.x || c.y == t.x || c.z == t.x || c.w == t.x || c.x == t.z || c.y == t.z || c.z == t.z || c.w == t.z;
+            carry_hit = carry_hit || (pvl == t.x && x0 == t.y) || (pvl == t.z && x0 == t.w);
+        }
     mi = 0;
     if (hit)
     {
-#pragma unroll 1
-        for (u32 i = 0; i < nb; i++)
+#pragma unroll
+        for (int q = 0; q < BATCH_MAX / 2; q++)
+            if ((u32)(2 * q) < nb)
             {
-                const u32 a = ra[i], b = rb[i];
-                if (c.x == a && c.y == b)
-                    mi |= (i + 1);
-                if (c.y == a && c.z == b)
-                    mi |= (i + 1) << 4;
-                if (c.z == a && c.w == b)
-                    mi |= (i + 1) << 8;
-                if (c.w == a && nx == b)
-                    mi |= (i + 1) << 12;
+                const uint4 t = p4[q];
+                if (c.x == t.x && c.y == t.y)
+                    mi |= (2 * q + 1);
+                if (c.y == t.x && c.z == t.y)
+                    mi |= (2 * q + 1) << 4;
+                if (c.z == t.x && c.w == t.y)
+                    mi |= (2 * q + 1) << 8;
+                if (c.w == t.x && nx == t.y)
+                    mi |= (2 * q + 1) << 12;
+                if (c.x == t.z && c.y == t.w)
+                    mi |= (2 * q + 2);
+                if (c.y == t.z && c.z == t.w)
+                    mi |= (2 * q + 2) << 4;
+                if (c.z == t.z && c.w == t.w)
+                    mi |= (2 * q + 2) << 8;
+                if (c.w == t.z && nx == t.w)
+                    mi |= (2 * q + 2) << 12;
             }
     }
     const u32 carry = carry_hit ? 1u : 0u;
@@ -268,6 +280,7 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
     __shared__ StageMeta s_meta[NST];
     __shared__ u32 s_halo[5]; // tokens at range positions -2, -1, n, n+1, n+2
     __shared__ u32 s_ba[BATCH_MAX], s_bb[BATCH_MAX];
+    __shared__ __align__(16) u32 s_ab[2 * BATCH_MAX]; // the same pairs interleaved (a0, b0, a1, b1, ...)
 
     const u32 *__restrict__ in = st->tok[ibuf] + (u64)cta * rcap;
     u32 *__restrict__ out = st->tok[obuf] + (u64)cta * rcap;
@@ -296,6 +309,8 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
     {
         s_ba[tid] = (tid < (int)nb) ? st->ba[tid] : SENT;
         s_bb[tid] = (tid < (int)nb) ? st->bb[tid] : SENT;
+        s_ab[2 * tid] = s_ba[tid];
+        s_ab[2 * tid + 1] = s_bb[tid];
     }
     __syncthreads();
 
@@ -429,7 +444,7 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
                 const uint4 c = *reinterpret_cast<const uint4 *>(sin + j * 128 + lane * 4);
                 u32 bits, v, mi = 0, ktj = 128;
                 const bool slow_it = (nb == 1) ? iter_bits(sin, j, lane, a, b, valid, full, c, bits, v)
-                                               : iter_bits_multi(sin, j, lane, nb, s_ba, s_bb, valid, full, c, bits, v, mi);
+                                               : iter_bits_multi(sin, j, lane, nb, s_ab, valid, full, c, bits, v, mi);
                 if (slow_it)
                 {
                     slow |= 1u << j;
@@ -611,7 +626,7 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
                         v = full ? 4u : ((p >= valid) ? 0u : ((valid - p < 4u) ? (valid - p) : 4u));
                     }
                     else
-                        iter_bits_multi(sin, j, lane, nb, s_ba, s_bb, valid, full, c, bits, v, mi);
+                        iter_bits_multi(sin, j, lane, nb, s_ab, valid, full, c, bits, v, mi);
                     const u32 keep = keep_mask(bits, v);
                     const u32 kc = (u32)__popc(keep);
                     // exclusive prefix of the kept counts (0..4 each) from three ballots
