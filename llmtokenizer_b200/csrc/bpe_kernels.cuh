@@ -1679,9 +1679,11 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
                         bl = l2;
                     }
                 }
-                if (bk == 0)
+                if (bk == 0 || (u32)(bk >> 32) < st->cand_T)
                 {
-                    bound = st->cand_T - 1; // the list is exhausted: everything else is below the threshold
+                    // The list is only complete for counts >= cand_T: entries that have decayed below the threshold
+                    // say nothing about the pairs that were never listed.  Everything else is below the threshold.
+                    bound = st->cand_T - 1;
                     break;
                 }
                 // same-bucket tie: another list's head, or the winner list's next entry, has the same packed key

@@ -111,6 +111,24 @@ def test_ranged_stream_boundaries(engine, oracle, ranges):
         assert np.array_equal(t2, ot), f"encode case {i} ranges {ranges}: {st}"
 
 
+def test_batched_passes_long_runs(engine, oracle):
+    """Late in training most passes carry several provably-next merges (batched passes).  Long
+    capped runs on corpora that stay above 1,048,576 tokens: the merge ORDER (ids) must be the sequential one."""
+    for kind, size, seed, cap in ((0, 12_000_000, 71, 2500), (1, 8_000_000, 72, 2200), (0, 9_000_000, 73, 2000)):
+        data = corpus(kind, size, seed)
+        m, t, st = assert_same(engine, oracle, data, cap=cap, what=f"kind {kind} {size} B / {cap} merges")
+        if kind == 0:   # (merges share passes once the ids have outgrown the shared-memory delta histogram)
+            assert st["batch_merges"] > 0 and st["replace_passes"] < cap, st
+        # and with batching off the very same result
+        ctx = engine.Context(0)
+        ctx.set_option("batch_max", 1)
+        ctx.upload(data)
+        s1 = ctx.train(cap)
+        m1, t1 = ctx.download()
+        ctx.close()
+        assert s1["batch_merges"] == 0 and np.array_equal(m1, m) and np.array_equal(t1, t)
+
+
 def test_encode_matches_training_ids_and_oracle(engine, oracle):
     data = corpus(0, 1_500_000, 5)
     m, t, _ = engine.train(data, max_merges=400)
