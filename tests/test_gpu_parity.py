@@ -129,6 +129,16 @@ def test_batched_passes_long_runs(engine, oracle):
         assert s1["batch_merges"] == 0 and np.array_equal(m1, m) and np.array_equal(t1, t)
 
 
+def test_batched_passes_with_many_ties(engine, oracle):
+    """Nearly uniform symbols: late merges all have almost the same count, so the order inside and between
+    batches is decided by the bucket order again and again (and now and then by a same-bucket tie, which
+    must end a batch and go through the exact resolver)."""
+    rng = np.random.default_rng(4)
+    data = rng.integers(33, 127, 14_000_000, dtype=np.uint8)
+    m, t, st = assert_same(engine, oracle, data, cap=2600, what="uniform 94 symbols, 14 MB / 2600 merges")
+    assert st["replace_passes"] <= 2600
+
+
 def test_encode_matches_training_ids_and_oracle(engine, oracle):
     data = corpus(0, 1_500_000, 5)
     m, t, _ = engine.train(data, max_merges=400)
