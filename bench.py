@@ -164,7 +164,7 @@ def bench_reference(args, w, rank, world):
     _, arr = make_corpus(w, pinned=False)
     path = f"/tmp/bench_corpus_{args.workload}.bin"
     arr.tofile(path)
-    sample = w["ref_sample_merges"]
+    sample = int(os.environ.get("BPE_BENCH_REF_MERGES") or w["ref_sample_merges"])
     for _ in range(args.warmup):
         run_reference_sample(path, sample)
     done_tot, sec_tot, kind = 0, 0.0, "reference"
