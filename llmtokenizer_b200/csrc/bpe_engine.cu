@@ -122,6 +122,7 @@ struct bpe_cuda_ctx
     DevState *h_st = nullptr;              // the latest copy of the control block (one of h_buf)
     DevState *h_buf[2] = {nullptr, nullptr}; // pinned
     cudaEvent_t poll_ev[2] = {nullptr, nullptr};
+    int pdl = 1;                             // programmatic dependent launch between the step kernels
     int speculate = 1;                       // enqueue the next batch before the current one has been polled
     // ranged layout: per buffer, length and edge tokens of every range
     u32 *d_rcnt[2] = {nullptr, nullptr};
@@ -512,6 +513,25 @@ static int ensure_resolver(bpe_cuda_ctx *c, u64 n, u32 slices)
     return 0;
 }
 
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait in bpe_kernels.cuh): the step kernels
+// follow one another, so each may be scheduled while its predecessor drains.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chained(bpe_cuda_ctx *c, void (*kernel)(KArgs...), int grid, int block, size_t smem, Args... args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = c->pdl ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // profiling marks: the interval that ends at a mark is charged to the mark's class
 enum
 {
@@ -621,9 +641,10 @@ static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool c
         // the histogram always gets its full budget: the device may be ahead of this id estimate, or batch merges
         const size_t vsmem = stream_smem_bytes(hist, hist ? (u32)c->smem_hist_max_vocab - 1 : 0);
         if (hist)
-            replace_stream_kernel<true><<<c->rmax, V_THREADS, vsmem, c->stream>>>(c->d_st, c->d_delta, (u32)(4 * c->smem_hist_max_vocab));
+            CU(launch_chained(c, replace_stream_kernel<true>, c->rmax, V_THREADS, vsmem, c->d_st, c->d_delta,
+                              (u32)(4 * c->smem_hist_max_vocab)));
         else
-            replace_stream_kernel<false><<<c->rmax, V_THREADS, vsmem, c->stream>>>(c->d_st, c->d_delta, 0);
+            CU(launch_chained(c, replace_stream_kernel<false>, c->rmax, V_THREADS, vsmem, c->d_st, c->d_delta, 0u));
     }
     else
     {
@@ -658,7 +679,7 @@ static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool c
         // every thread looks at one token's four counters (128 bits) per trip; 32 blocks keep the "last block" wait short
         // (batches are mostly short: size the grid for two merges, the loop is grid-stride)
         const int agrid = (int)std::min<u64>((std::min<u64>(eff_batch(c), 2) * 4ull * (z + 1) + SEL_THREADS - 1) / SEL_THREADS, 64);
-        apply_select_kernel<<<agrid + 1, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_delta_red, c->d_delta, encode ? 1 : 0);
+        CU(launch_chained(c, apply_select_kernel, agrid + 1, SEL_THREADS, 0, c->d_st, c->d_delta_red, c->d_delta, encode ? 1 : 0));
         c->launches++;
         prof_mark(c, PT_APPLY);
     }
@@ -1381,6 +1402,8 @@ int bpe_cuda_ctx_create(int device, bpe_cuda_ctx_t **out)
         c->batch_max = atoi(e);
     if (const char *e = getenv("BPE_CUDA_RANGES"))
         c->ranges_opt = atoi(e);
+    if (const char *e = getenv("BPE_CUDA_PDL"))
+        c->pdl = atoi(e) != 0;
     if (const char *e = getenv("BPE_CUDA_SPECULATE"))
         c->speculate = atoi(e) != 0;
     *out = c;
@@ -1585,6 +1608,8 @@ int bpe_cuda_ctx_set_option(bpe_cuda_ctx_t *c, const char *name, long long value
         c->batch_max = (int)value;
     else if (!strcmp(name, "ranges"))
         c->ranges_opt = (int)value;
+    else if (!strcmp(name, "pdl"))
+        c->pdl = (int)(value != 0);
     else if (!strcmp(name, "speculate"))
         c->speculate = (int)(value != 0);
     else if (!strcmp(name, "use_stream"))

@@ -137,7 +137,13 @@ struct DevState
 
 // ---------------------------------------------------------------------------------------------
 // hash_table.c:8-53 on the 8-byte key {u32 a; u32 b}
-__host__ __device__ __forceinline__ u64 gtime()
+__host__ // Programmatic dependent launch: a kernel launched with the "programmatic stream serialization" attribute may be
+// scheduled while its predecessor is still running; pdl_wait() blocks until the predecessor has completed and its
+// writes are visible (a no-op for a normal launch), pdl_launch_dependents() lets the successor's CTAs be scheduled.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ u64 gtime()
 {
     u64 t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -1458,6 +1464,8 @@ __global__ void __launch_bounds__(256) apply_kernel(DevState *st, int32_t *delta
 // decides.  encode: the next rank of the given merge list instead of the maximum.
 __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st, int32_t *delta_in, int32_t *delta_local, int encode)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     if (st->stop != STOP_RUN)
         return;
     __shared__ SelPart sm[SEL_THREADS / 32];

@@ -250,6 +250,8 @@ template <bool SMEM_HIST>
 __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *st, int32_t *delta, u32 hist_words)
 {
     constexpr int NST = SMEM_HIST ? V_STAGES_HIST : V_STAGES;
+    pdl_wait();
+    pdl_launch_dependents();
     if (st->stop != STOP_RUN || st->skip)
         return;
     const u32 a = st->a, b = st->b, z = st->z, nb = st->nb;
