@@ -290,6 +290,15 @@ def bench_engine(args, w, rank, world, local):
     roofline["whole_step_gbs"] = whole
     roofline["whole_step_frac"] = whole / peak
 
+    # ---- encode GB/s: apply the learned merge table to the same corpus (resident; N = 1 only) ------
+    encode = None
+    if world == 1:
+        merges_np, _ = ctx.download(tokens=False)
+        se = ctx.encode(merges_np)
+        se = ctx.encode(merges_np)
+        encode = {"value": shard.size / (se["ms_device"] * 1e-3) / 1e9, "unit": "GB/s of input", "ranks": int(len(merges_np)),
+                  "ms": se["ms_device"], "passes": se["replace_passes"]}
+
     # ---- CPU reference beside it (rank 0, N = 1 only) ---------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -317,6 +326,7 @@ def bench_engine(args, w, rank, world, local):
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "encode": encode,
             "engine_stats": {k: sp[k] for k in ("same_bucket_ties", "threshold_edges", "resolver_runs", "census_runs",
                                                  "table_rehashes", "table_capacity", "final_distinct", "replace_passes",
                                                  "batch_merges", "batch_passes")},

@@ -208,11 +208,11 @@ static inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; 
 // identically on every rank).
 static inline size_t eff_batch(const bpe_cuda_ctx *c)
 {
-    if (c->run_encode)
-        return 1;
     const int bm = std::max(1, std::min(c->batch_max, (int)BATCH_MAX));
     if (c->world == 1)
         return (size_t)bm;
+    if (c->run_encode)
+        return 1;
     return (c->run_max_merges != 0 && c->run_max_merges <= 8192 - 256) ? (size_t)std::min(bm, 4) : 1;
 }
 
@@ -727,7 +727,7 @@ static u64 batch_steps_for(bpe_cuda_ctx *c, const DevState *h, bool encode, u64 
         G = (h->max_merges + 1 > m1) ? std::min<u64>(G, h->max_merges - m1 + 1) : 0;
     if (encode)
         G = (h->enc_total + 1 > m1) ? std::min<u64>(G, h->enc_total - m1 + 1) : 0;
-    while (G > 4 && batch_margin(G, z0, eff_batch(c), h->freq) > c->tcap / 4)
+    while (G > 4 && batch_margin(G, z0, eff_batch(c), encode ? 0 : h->freq) > c->tcap / 4)
         G /= 2;
     return G;
 }
@@ -806,7 +806,7 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
         X.zub0 = X.z0;
         X.G = batch_steps_for(c, h, encode, X.m1, X.z0);
         const u64 bm = eff_batch(c);
-        X.margin = batch_margin(X.G, X.z0, bm, h->freq);
+        X.margin = batch_margin(X.G, X.z0, bm, encode ? 0 : h->freq);
         X.n_upper = h->n;
         // table growth: bounded by the headroom two batches may consume (<= 2*(V+1) new keys a step)
         if (h->occupied + 2 * X.margin > c->tcap / 2 + c->tcap / 8)
@@ -888,7 +888,7 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
             Y.zub0 = z_ub;
             Y.pending = true;
             Y.G = batch_steps_for(c, prev, encode, Y.m1, Y.z0);
-            Y.margin = batch_margin(Y.G, Y.z0, bm, prev->freq);
+            Y.margin = batch_margin(Y.G, Y.z0, bm, encode ? 0 : prev->freq);
             Y.n_upper = X.n_upper;
             Y.census = false;
             Y.ranged = X.ranged;

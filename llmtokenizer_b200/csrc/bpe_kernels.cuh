@@ -849,6 +849,27 @@ __device__ inline void decide_rank(DevState *st, const int32_t *delta_reduced)
             st->pause = PAUSE_SAME;
             st->stop = STOP_PAUSE;
         }
+        else if (a != b && st->batch_max > 1 && st->want_ranged && !st->static_mode && st->z >= st->batch_min_z)
+        {
+            // The following ranks can share this pass as long as nothing connects them: pairwise different tokens,
+            // none of them an id that this very pass creates, no a == a pair.  (No counts are involved here: the
+            // merge list is given, only the ORDER of application must not matter.)
+            const u32 z_first = st->z;
+            u32 jcap = min(st->batch_max, (u32)BATCH_MAX);
+            for (u64 r2 = r + 1; r2 < st->enc_total && st->nb < jcap; r2++)
+            {
+                const u32 a2 = st->enc_merges[2 * r2], b2 = st->enc_merges[2 * r2 + 1];
+                bool ok = a2 != b2 && a2 < z_first && b2 < z_first;
+                for (u32 i = 0; ok && i < st->nb; i++)
+                    ok = a2 != st->ba[i] && a2 != st->bb[i] && b2 != st->ba[i] && b2 != st->bb[i];
+                if (!ok)
+                    break;
+                extend_batch(st, a2, b2);
+                st->ranks_applied++;
+            }
+            if (st->nb > 1)
+                st->batch_passes++;
+        }
     }
 }
 

@@ -127,6 +127,12 @@ def test_batched_passes_long_runs(engine, oracle):
         m1, t1 = ctx.download()
         ctx.close()
         assert s1["batch_merges"] == 0 and np.array_equal(m1, m) and np.array_equal(t1, t)
+        # encoding batches consecutive ranks with unconnected tokens: same ids as training, and as the oracle elsewhere
+        ids, se = engine.encode(data, m)
+        assert np.array_equal(ids, t), se
+        other = corpus(kind, 3_000_000, seed + 100)
+        ids2, _ = engine.encode(other, m)
+        assert np.array_equal(ids2, oracle.encode(other, m))
 
 
 def test_batched_passes_with_many_ties(engine, oracle):
