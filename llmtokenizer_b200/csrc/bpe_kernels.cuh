@@ -849,7 +849,8 @@ __device__ inline void decide_rank(DevState *st, const int32_t *delta_reduced)
             st->pause = PAUSE_SAME;
             st->stop = STOP_PAUSE;
         }
-        else if (a != b && st->batch_max > 1 && st->want_ranged && !st->static_mode && st->z >= st->batch_min_z)
+        else if (a != b && st->batch_max > 1 && st->want_ranged && !st->static_mode && st->z >= st->batch_min_z &&
+                 st->z >= st->hist_max)
         {
             // The following ranks can share this pass as long as nothing connects them: pairwise different tokens,
             // none of them an id that this very pass creates, no a == a pair.  (No counts are involved here: the
@@ -1618,7 +1619,8 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
         t6 = gtime();
         // A committed a != b merge on a RANGED stream may take the next merges along in its pass.
         const bool extend = fits && st->stop == STOP_RUN && st->pending && st->batch_max > 1 && st->cand_T && st->want_ranged &&
-                            !st->static_mode && st->a != st->b && st->z >= st->batch_min_z && st->merges_done < st->max_merges;
+                            !st->static_mode && st->a != st->b && st->z >= st->batch_min_z && st->z >= st->hist_max &&
+                            st->merges_done < st->max_merges;
         s_win = extend ? s : NO_SLOT;
     }
     __syncthreads();

@@ -254,11 +254,21 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
     pdl_launch_dependents();
     if (st->stop != STOP_RUN || st->skip)
         return;
-    const u32 a = st->a, b = st->b, z = st->z, nb = st->nb;
+    // Two specialisations keep each variant's code small (the kernel is instruction-bound on replacement-heavy
+    // passes and ncu shows instruction-cache misses): <true> = one merge, deltas privatised in shared memory (the
+    // host launches it only while ids are below hist_max, where passes are never batched); <false> = up to BATCH_MAX
+    // merges, deltas straight to global memory.
+    const u32 a = st->a, b = st->b, z = st->z;
+    const u32 nb = SMEM_HIST ? 1u : st->nb;
     const u32 VS = z + nb; // delta block stride, see apply_deltas
-    // the host gave the shared-memory delta histogram hist_words counters: enough for this (batch of) merge(s)?
-    const u32 hist_need = nb * 4 * VS;
-    const bool use_hist = SMEM_HIST && hist_need <= hist_words;
+    const u32 hist_need = 4 * VS;
+    constexpr bool use_hist = SMEM_HIST;
+    if (SMEM_HIST && (st->nb != 1 || hist_need > hist_words))
+    {
+        if (threadIdx.x == 0)
+            atomicOr(&st->err, ERR_PROBE); // host / device disagree about the regime: fail loudly
+        return;
+    }
     const u32 cta = blockIdx.x, nr = st->nr;
     if (a == b || st->layout != LAYOUT_RANGED)
     {
