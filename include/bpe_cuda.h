@@ -14,6 +14,9 @@
  *   bpe_cuda_ctx_*            the same two operations split into upload / run / download so a
  *                             caller (bench, multi-process ranks) can keep the corpus resident in
  *                             HBM and shard it across GPUs; additive
+ *   bpe_cuda_decode           bpe/src/bpe.c:341-394 decompress() with resolve_pair() bpe.c:23-92: ids ->
+ *   bpe_cuda_ctx_decode*      bytes through the merge list; byte-exact and NUL-safe (explicit lengths
+ *                             instead of the reference's NUL-terminated memo strings)
  *   bpe_cuda_free             free() of compress()'s outputs (main.c:22)
  *   bpe_cuda_last_error       perror/printf diagnostics of bpe.c:133-171,560
  *
@@ -86,6 +89,11 @@ int bpe_cuda_train(const uint8_t *bytes, size_t n, uint64_t max_merges, int n_gp
 int bpe_cuda_encode(const uint8_t *bytes, size_t n, const bpe_pair_t *merges, size_t n_merges, int n_gpus,
                     uint32_t **tokens_out, size_t *n_tokens, bpe_cuda_stats_t *stats);
 
+/* Inverse of encode: expand tokens[0..n_tokens) through the merge list (id 256+r -> merges[r]).
+ * *bytes_out holds *n_bytes bytes plus one terminating 0 like decompress()'s string (bpe.c:390). */
+int bpe_cuda_decode(const uint32_t *tokens, size_t n_tokens, const bpe_pair_t *merges, size_t n_merges, uint8_t **bytes_out,
+                    size_t *n_bytes, bpe_cuda_stats_t *stats);
+
 void bpe_cuda_free(void *p);
 const char *bpe_cuda_last_error(void);
 int bpe_cuda_device_count(void);
@@ -115,6 +123,15 @@ int bpe_cuda_ctx_result_sizes(bpe_cuda_ctx_t *ctx, size_t *n_merges, size_t *n_t
 int bpe_cuda_ctx_download(bpe_cuda_ctx_t *ctx, bpe_pair_t *merges, uint32_t *tokens_local);
 /* device pointer to this rank's token stream after the last run (valid until the next run) */
 const uint32_t *bpe_cuda_ctx_device_tokens(bpe_cuda_ctx_t *ctx);
+
+/* Decode this rank's token stream of the last run without leaving the device; the bytes stay in HBM
+ * (bpe_cuda_ctx_device_decoded) until the next decode.  _compare counts the bytes that differ from
+ * the resident shard (UINT64_MAX when the lengths differ): the round trip decode(encode(x)) == x at
+ * full scale with no host copy.  Shards decode independently: no collective. */
+int bpe_cuda_ctx_decode(bpe_cuda_ctx_t *ctx, const bpe_pair_t *merges, size_t n_merges, size_t *n_bytes);
+int bpe_cuda_ctx_decode_download(bpe_cuda_ctx_t *ctx, uint8_t *bytes);
+int bpe_cuda_ctx_decode_compare(bpe_cuda_ctx_t *ctx, uint64_t *n_diff);
+const uint8_t *bpe_cuda_ctx_device_decoded(bpe_cuda_ctx_t *ctx);
 
 /* knobs: "profile_replace" (0/1), "batch_steps" (merge steps enqueued per host poll),
  * "smem_hist_max_vocab", "force_census" (0/1).  Returns 0 if the knob exists. */

@@ -31,7 +31,8 @@ EXPORTS = [
     "bpe_cuda_ctx_create", "bpe_cuda_ctx_destroy", "bpe_cuda_nccl_unique_id", "bpe_cuda_ctx_set_comm",
     "bpe_cuda_ctx_upload", "bpe_cuda_ctx_upload_device", "bpe_cuda_ctx_train", "bpe_cuda_ctx_encode",
     "bpe_cuda_ctx_result_sizes", "bpe_cuda_ctx_download", "bpe_cuda_ctx_device_tokens", "bpe_cuda_ctx_set_option",
-    "bpe_cuda_decode", "bpe_cuda_ctx_decode",
+    "bpe_cuda_decode", "bpe_cuda_ctx_decode", "bpe_cuda_ctx_decode_download", "bpe_cuda_ctx_decode_compare",
+    "bpe_cuda_ctx_device_decoded",
 ]
 
 _lib = None
@@ -81,10 +82,16 @@ def load():
     lib.bpe_cuda_ctx_device_tokens.restype = C.c_void_p
     lib.bpe_cuda_ctx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong]
     lib.bpe_cuda_ctx_set_option.restype = C.c_int
-    if hasattr(lib, "bpe_cuda_decode"):
-        lib.bpe_cuda_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, P(P(C.c_uint8)), P(C.c_size_t),
-                                        P(Stats)]
-        lib.bpe_cuda_decode.restype = C.c_int
+    lib.bpe_cuda_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, P(P(C.c_uint8)), P(C.c_size_t), P(Stats)]
+    lib.bpe_cuda_decode.restype = C.c_int
+    lib.bpe_cuda_ctx_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, P(C.c_size_t)]
+    lib.bpe_cuda_ctx_decode.restype = C.c_int
+    lib.bpe_cuda_ctx_decode_download.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bpe_cuda_ctx_decode_download.restype = C.c_int
+    lib.bpe_cuda_ctx_decode_compare.argtypes = [C.c_void_p, P(C.c_uint64)]
+    lib.bpe_cuda_ctx_decode_compare.restype = C.c_int
+    lib.bpe_cuda_ctx_device_decoded.argtypes = [C.c_void_p]
+    lib.bpe_cuda_ctx_device_decoded.restype = C.c_void_p
     _lib = lib
     return lib
 

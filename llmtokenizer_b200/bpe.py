@@ -82,6 +82,25 @@ def encode(data, merges, n_gpus=1):
     return t, st.as_dict()
 
 
+def decode(tokens, merges):
+    """ids -> bytes through the merge list (what decompress() computes, bpe.c:341-394) -> (bytes, stats)."""
+    lib = _lib.load()
+    tk = np.ascontiguousarray(np.asarray(tokens, dtype=np.uint32).reshape(-1))
+    mg = np.ascontiguousarray(np.asarray(merges, dtype=np.uint32).reshape(-1, 2))
+    out = C.POINTER(C.c_uint8)()
+    nb = C.c_size_t()
+    st = Stats()
+    rc = lib.bpe_cuda_decode(tk.ctypes.data if tk.size else None, tk.size, mg.ctypes.data if mg.size else None, mg.shape[0],
+                             C.byref(out), C.byref(nb), C.byref(st))
+    if rc:
+        raise BpeCudaError(rc)
+    try:
+        b = C.string_at(out, nb.value)
+    finally:
+        lib.bpe_cuda_free(out)
+    return b, st.as_dict()
+
+
 class Context:
     """One GPU: keeps a corpus shard resident in HBM; train/encode can run on it repeatedly."""
 
@@ -143,6 +162,29 @@ class Context:
         if rc:
             raise BpeCudaError(rc)
         return st.as_dict()
+
+    def decode(self, merges, download=True):
+        """Expand this rank's token stream of the last run on the device -> bytes (or their count)."""
+        mg = np.ascontiguousarray(np.asarray(merges, dtype=np.uint32).reshape(-1, 2))
+        nb = C.c_size_t()
+        rc = self.lib.bpe_cuda_ctx_decode(self.h, mg.ctypes.data if mg.size else None, mg.shape[0], C.byref(nb))
+        if rc:
+            raise BpeCudaError(rc)
+        if not download:
+            return nb.value
+        buf = np.zeros(nb.value, dtype=np.uint8)
+        rc = self.lib.bpe_cuda_ctx_decode_download(self.h, buf.ctypes.data if nb.value else None)
+        if rc:
+            raise BpeCudaError(rc)
+        return buf.tobytes()
+
+    def decode_mismatches(self):
+        """Bytes of the last decode that differ from the resident shard (compared on the device)."""
+        d = C.c_uint64()
+        rc = self.lib.bpe_cuda_ctx_decode_compare(self.h, C.byref(d))
+        if rc:
+            raise BpeCudaError(rc)
+        return d.value
 
     def result_sizes(self):
         nm, nt = C.c_size_t(), C.c_size_t()

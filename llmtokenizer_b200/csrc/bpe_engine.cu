@@ -10,6 +10,7 @@
 #include "bpe_kernels.cuh"
 #include "bpe_replace.cuh"
 #include "bpe_resolver.cuh"
+#include "bpe_decode.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -174,6 +175,11 @@ struct bpe_cuda_ctx
     // exact tie-break machinery (bpe_resolver.cuh)
     ResState *d_rs = nullptr;
     u64 *d_first = nullptr;
+    // decode: flattened vocabulary, tile offsets, output bytes
+    u32 *d_dec_len = nullptr, *d_dec_off = nullptr;
+    uint8_t *d_dec_blob = nullptr, *d_dec_out = nullptr;
+    u64 *d_dec_tiles = nullptr;
+    size_t dec_vocab_cap = 0, dec_blob_cap = 0, dec_out_cap = 0, dec_tiles_cap = 0, dec_n_out = 0;
     u32 *d_rank = nullptr;
     size_t first_cap = 0; // entries (slots * slices)
     u32 *d_pos_slot = nullptr;
@@ -1451,6 +1457,11 @@ void bpe_cuda_ctx_destroy(bpe_cuda_ctx_t *c)
     cudaFree(c->d_dense);
     cudaFree(c->d_rs);
     cudaFree(c->d_first);
+    cudaFree(c->d_dec_len);
+    cudaFree(c->d_dec_off);
+    cudaFree(c->d_dec_blob);
+    cudaFree(c->d_dec_out);
+    cudaFree(c->d_dec_tiles);
     cudaFree(c->d_rank);
     cudaFree(c->d_pos_slot);
     cudaFree(c->d_tile_cnt);
@@ -1616,6 +1627,227 @@ int bpe_cuda_ctx_set_option(bpe_cuda_ctx_t *c, const char *name, long long value
         c->use_stream = (int)(value != 0);
     else
         return BPE_CUDA_ERR_ARG;
+    return 0;
+}
+
+// ---- decode (reference bpe/src/bpe.c:23-92, 341-394) --------------------
+// Flatten the vocabulary on the host: id < 256 is its own byte, id 256+r is expansion(a) ++ expansion(b)
+// (resolve_pair, bpe.c:23-92, without the NUL-terminated strings).
+static int decode_flatten(const bpe_pair_t *merges, size_t n_merges, std::vector<u32> &len, std::vector<u32> &off,
+                          std::vector<uint8_t> &blob)
+{
+    const size_t V = 256 + n_merges;
+    len.resize(V);
+    off.resize(V);
+    u64 total = 256;
+    for (size_t i = 0; i < 256; i++)
+    {
+        len[i] = 1;
+        off[i] = (u32)i;
+    }
+    for (size_t r = 0; r < n_merges; r++)
+    {
+        const u32 a = merges[r].a, b = merges[r].b;
+        if (a >= 256 + r || b >= 256 + r)
+        {
+            set_error("merge %zu refers to an id that does not exist yet", r);
+            return BPE_CUDA_ERR_ARG;
+        }
+        const u64 l = (u64)len[a] + len[b];
+        if (total + l > (1ull << 30))
+        {
+            set_error("decode: the flattened vocabulary exceeds 1 GiB");
+            return BPE_CUDA_ERR_NOMEM;
+        }
+        len[256 + r] = (u32)l;
+        off[256 + r] = (u32)total;
+        total += l;
+    }
+    blob.resize(total);
+    for (size_t i = 0; i < 256; i++)
+        blob[i] = (uint8_t)i;
+    for (size_t r = 0; r < n_merges; r++)
+    {
+        const u32 a = merges[r].a, b = merges[r].b;
+        memcpy(&blob[off[256 + r]], &blob[off[a]], len[a]);
+        memcpy(&blob[off[256 + r] + len[a]], &blob[off[b]], len[b]);
+    }
+    return 0;
+}
+
+extern "C++"
+{
+template <class T> static int dec_reserve(T *&p, size_t &cap, size_t need)
+{
+    if (need <= cap)
+        return 0;
+    if (p)
+        CU(cudaFree(p));
+    p = nullptr;
+    cap = 0;
+    const size_t want = need + need / 8 + 256;
+    CU(cudaMalloc(&p, want * sizeof(T)));
+    cap = want;
+    return 0;
+}
+}
+
+// Expand d_tok[0..n) (device) into c->d_dec_out; *n_bytes = size of the expansion.
+static int decode_device(bpe_cuda_ctx *c, const u32 *d_tok, u64 n, const bpe_pair_t *merges, size_t n_merges, size_t *n_bytes)
+{
+    int rc;
+    CU(cudaSetDevice(c->device));
+    std::vector<u32> len, off;
+    std::vector<uint8_t> blob;
+    if ((rc = decode_flatten(merges, n_merges, len, off, blob)))
+        return rc;
+    const size_t V = len.size();
+    const u64 nt = (n + DEC_TILE - 1) / DEC_TILE;
+    size_t cap2 = c->dec_vocab_cap;
+    if ((rc = dec_reserve(c->d_dec_len, c->dec_vocab_cap, V)) || (rc = dec_reserve(c->d_dec_off, cap2, V)) ||
+        (rc = dec_reserve(c->d_dec_blob, c->dec_blob_cap, blob.size())) ||
+        (rc = dec_reserve(c->d_dec_tiles, c->dec_tiles_cap, nt + 2)))
+        return rc;
+    CU(cudaMemcpyAsync(c->d_dec_len, len.data(), V * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_dec_off, off.data(), V * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_dec_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, c->stream));
+    u64 *d_total = c->d_dec_tiles + nt;     // written by the scan
+    u32 *d_err = reinterpret_cast<u32 *>(c->d_dec_tiles + nt + 1);
+    CU(cudaMemsetAsync(c->d_dec_tiles + nt, 0, 2 * sizeof(u64), c->stream));
+    DecodeVocab v{c->d_dec_len, c->d_dec_off, c->d_dec_blob, (u32)V};
+    c->dec_n_out = 0;
+    if (n)
+    {
+        decode_len_kernel<<<(unsigned)nt, DEC_THREADS, 0, c->stream>>>(d_tok, n, v, c->d_dec_tiles, d_err);
+        decode_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_dec_tiles, nt);
+        c->launches += 2;
+    }
+    u64 h[2] = {0, 0};
+    CU(cudaMemcpyAsync(h, d_total, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if ((u32)h[1])
+    {
+        set_error("decode: the stream holds an id outside the vocabulary (%zu entries)", V);
+        return BPE_CUDA_ERR_ARG;
+    }
+    if ((rc = dec_reserve(c->d_dec_out, c->dec_out_cap, (size_t)h[0] + 16)))
+        return rc;
+    if (n)
+    {
+        decode_expand_kernel<<<(unsigned)nt, DEC_THREADS, 0, c->stream>>>(d_tok, n, v, c->d_dec_tiles, c->d_dec_out);
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    c->dec_n_out = (size_t)h[0];
+    if (n_bytes)
+        *n_bytes = (size_t)h[0];
+    return 0;
+}
+
+int bpe_cuda_ctx_decode(bpe_cuda_ctx_t *c, const bpe_pair_t *merges, size_t n_merges, size_t *n_bytes)
+{
+    if (!c || (!merges && n_merges) || !c->h_st)
+        return BPE_CUDA_ERR_ARG;
+    return decode_device(c, c->h_st->tok[c->h_st->cur], c->res_n_tokens, merges, n_merges, n_bytes);
+}
+
+int bpe_cuda_ctx_decode_download(bpe_cuda_ctx_t *c, uint8_t *bytes)
+{
+    if (!c || (!bytes && c->dec_n_out))
+        return BPE_CUDA_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    if (c->dec_n_out)
+        CU(cudaMemcpyAsync(bytes, c->d_dec_out, c->dec_n_out, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int bpe_cuda_ctx_decode_compare(bpe_cuda_ctx_t *c, uint64_t *n_diff)
+{
+    if (!c || !n_diff)
+        return BPE_CUDA_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    if (c->dec_n_out != c->n_bytes)
+    {
+        *n_diff = UINT64_MAX; // different lengths
+        return 0;
+    }
+    if (!c->n_bytes)
+    {
+        *n_diff = 0;
+        return 0;
+    }
+    u64 *d_diff = c->d_dec_tiles; // free again after the expansion
+    CU(cudaMemsetAsync(d_diff, 0, sizeof(u64), c->stream));
+    decode_compare_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_dec_out, c->d_bytes, c->n_bytes, d_diff);
+    c->launches++;
+    CU(cudaMemcpyAsync(n_diff, d_diff, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+const uint8_t *bpe_cuda_ctx_device_decoded(bpe_cuda_ctx_t *c)
+{
+    return c ? c->d_dec_out : nullptr;
+}
+
+int bpe_cuda_decode(const uint32_t *tokens, size_t n_tokens, const bpe_pair_t *merges, size_t n_merges, uint8_t **bytes_out,
+                    size_t *n_bytes, bpe_cuda_stats_t *stats)
+{
+    if ((!tokens && n_tokens) || (!merges && n_merges) || !bytes_out || !n_bytes)
+    {
+        set_error("invalid argument");
+        return BPE_CUDA_ERR_ARG;
+    }
+    *bytes_out = nullptr;
+    *n_bytes = 0;
+    bpe_cuda_ctx_t *c = nullptr;
+    int rc = bpe_cuda_ctx_create(0, &c);
+    if (rc)
+        return rc;
+    const auto t0 = std::chrono::steady_clock::now();
+    u32 *d_tok = nullptr;
+    uint8_t *out = nullptr;
+    size_t nb = 0;
+    auto body = [&]() -> int {
+        if (n_tokens)
+        {
+            CU(cudaMalloc(&d_tok, n_tokens * sizeof(u32)));
+            CU(cudaMemcpyAsync(d_tok, tokens, n_tokens * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+        }
+        int r = decode_device(c, d_tok, n_tokens, merges, n_merges, &nb);
+        if (r)
+            return r;
+        out = (uint8_t *)malloc(nb + 1); // +1: room for the terminator decompress() appends (bpe.c:390)
+        if (!out)
+        {
+            set_error("out of host memory");
+            return BPE_CUDA_ERR_NOMEM;
+        }
+        out[nb] = 0;
+        return bpe_cuda_ctx_decode_download(c, out);
+    };
+    rc = body();
+    if (d_tok)
+        cudaFree(d_tok);
+    if (stats)
+    {
+        memset(stats, 0, sizeof *stats);
+        stats->n_input = n_tokens;
+        stats->n_merges = n_merges;
+        stats->n_tokens = nb;
+        stats->kernel_launches = c->launches;
+        stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    bpe_cuda_ctx_destroy(c);
+    if (rc)
+    {
+        free(out);
+        return rc;
+    }
+    *bytes_out = out;
+    *n_bytes = nb;
     return 0;
 }
 

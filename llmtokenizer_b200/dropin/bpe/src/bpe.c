@@ -286,34 +286,35 @@ char *resolve_pair(uint32_t pair_index, dyn_arr_t *pair_arr, hash_table_t *memoi
 
 char *decompress(uint32_t *encoding, size_t len, dyn_arr_t *pair_arr) /* bpe.c:341-394 */
 {
-    if (!encoding || !pair_arr)
+    /* the expansion of the whole stream runs on the GPU (bpe_cuda_decode); the string it returns is
+     * NUL-terminated like the reference's (bpe.c:390) */
+    if (!encoding || !pair_arr || pair_arr->last_index < 255)
         return NULL;
-    size_t *L = expansion_lengths(pair_arr);
-    if (!L)
+    const size_t n_merges = pair_arr->last_index - 255;
+    bpe_pair_t *merges = (bpe_pair_t *)malloc((n_merges ? n_merges : 1) * sizeof *merges);
+    if (!merges)
         return NULL;
-    size_t total = 0;
-    for (size_t i = 0; i < len; i++)
+    for (size_t r = 0; r < n_merges; r++)
     {
-        if (encoding[i] > pair_arr->last_index || !L[encoding[i]])
+        pair_t p;
+        if (!dyn_arr_get(pair_arr, 256 + r, &p))
         {
-            free(L);
+            free(merges);
             return NULL;
         }
-        total += L[encoding[i]];
+        merges[r].a = p.a;
+        merges[r].b = p.b;
     }
-    free(L);
-    char *out = (char *)malloc(total + 1), *w = out;
-    if (!out)
-        return NULL;
-    for (size_t i = 0; i < len && w; i++)
-        w = expand_into(encoding[i], pair_arr, w);
-    if (!w)
+    uint8_t *bytes = NULL;
+    size_t n_bytes = 0;
+    const int rc = bpe_cuda_decode(encoding, len, merges, n_merges, &bytes, &n_bytes, NULL);
+    free(merges);
+    if (rc)
     {
-        free(out);
+        fprintf(stderr, "decompress: %s\n", bpe_cuda_last_error());
         return NULL;
     }
-    *w = '\0';
-    return out;
+    return (char *)bytes;
 }
 
 void render_pairs(dyn_arr_t *pair_arr) /* bpe.c:94-128 */

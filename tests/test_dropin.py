@@ -74,9 +74,12 @@ def test_host_side_decode_and_pair_file(lib, tmp_path):
     g = oracle_api.golden("testing_txt")
     arr = vocabulary(lib, g["merges"])
     assert arr.contents.last_index == 255 + len(g["merges"])
-    ids = np.ascontiguousarray(g["ids"], dtype=np.uint32)
-    s = lib.decompress(ids.ctypes.data, len(ids), arr)
-    assert s and C.string_at(s) == g["input"].tobytes()       # decompress(compress(x)) == x
+    # resolve_pair (bpe.c:23-92) is host code: the last id expands to what the oracle says
+    lib.resolve_pair.restype = C.c_void_p
+    lib.resolve_pair.argtypes = [C.c_uint32, C.POINTER(DynArr), C.c_void_p]
+    last = 255 + len(g["merges"])
+    s = lib.resolve_pair(last, arr, None)
+    assert s and C.string_at(s) == oracle_api.load().decode(np.array([last], np.uint32), g["merges"])
     C.CDLL(None).free(C.c_void_p(s))
     p = str(tmp_path / "pairs.bin").encode()
     assert lib.dump_pairs(p, arr)
@@ -88,6 +91,19 @@ def test_host_side_decode_and_pair_file(lib, tmp_path):
         assert lib.dyn_arr_get(back, k, C.byref(q)) and (q.a, q.b) == tuple(int(x) for x in g["merges"][k - 256])
     lib.dyn_arr_free(back)
     lib.dyn_arr_free(arr)
+
+
+@pytest.mark.gpu
+def test_decompress_inverts_compress(lib):
+    # decompress() (bpe.c:341-394) runs the GPU decode: decompress(compress(x)) == x
+    for name in ("testing_txt", "kat_k11"):
+        g = oracle_api.golden(name)
+        arr = vocabulary(lib, g["merges"])
+        ids = np.ascontiguousarray(g["ids"], dtype=np.uint32)
+        s = lib.decompress(ids.ctypes.data, len(ids), arr)
+        assert s and C.string_at(s) == g["input"].tobytes().split(b"\0")[0]
+        C.CDLL(None).free(C.c_void_p(s))
+        lib.dyn_arr_free(arr)
 
 
 def test_compress_argument_errors(lib, tmp_path):

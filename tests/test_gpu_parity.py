@@ -208,3 +208,66 @@ def test_sharded_training_and_encoding_match_oracle(engine, oracle, P):
     other = corpus(0, 2_000_001, 10)
     ids2, _ = engine.encode(other, m, n_gpus=P)
     assert np.array_equal(ids2, oracle.encode(other, m))
+
+
+# ---- decode: ids -> bytes, the inverse of the path ------------------------
+@pytest.mark.parametrize("kind,size,cap", [(0, 300_000, 600), (1, 200_000, 300), (2, 150_000, 200)])
+def test_decode_matches_oracle_and_round_trips(engine, oracle, kind, size, cap):
+    data = corpus(kind, size, 7 + kind)
+    m, t, _ = engine.train(data, max_merges=cap)
+    got, st = engine.decode(t, m)
+    assert got == oracle.decode(t, m)
+    cut = data.tobytes().split(b"\0")[0]
+    assert got == cut                      # decode(train(x).ids) == x
+    assert st["n_tokens"] == len(cut) and st["kernel_launches"] == 3
+    # a vocabulary prefix decodes ids produced by the same prefix
+    ids, _ = engine.encode(data, m[: cap // 2])
+    assert engine.decode(ids, m[: cap // 2])[0] == cut
+
+
+def test_decode_edge_cases(engine, oracle):
+    none = np.zeros((0, 2), np.uint32)
+    assert engine.decode(np.zeros(0, np.uint32), none)[0] == b""
+    raw = np.arange(256, dtype=np.uint32)          # every byte value, 0x00 included: NUL-safe
+    assert engine.decode(raw, none)[0] == bytes(range(256))
+    # a == b chains double the expansion: id 256+k is 2^(k+1) bytes, far beyond one staging tile
+    m = np.array([[97, 97]] + [[256 + k, 256 + k] for k in range(17)], dtype=np.uint32)
+    ids = np.array([273, 98, 256, 273, 0, 260], dtype=np.uint32)
+    got = engine.decode(ids, m)[0]
+    assert got == oracle.decode(ids, m) and len(got) == 2 * (1 << 18) + 1 + 2 + 1 + 32
+    with pytest.raises(engine.BpeCudaError) as e:   # id outside the vocabulary
+        engine.decode(np.array([97, 300], np.uint32), m[:3])
+    assert e.value.rc == -1
+    with pytest.raises(engine.BpeCudaError) as e:   # merge referring to a later id
+        engine.decode(np.array([97], np.uint32), np.array([[300, 97]], np.uint32))
+    assert e.value.rc == -1
+    # ragged sizes around the 2,048-id tile
+    rng = np.random.default_rng(5)
+    mm = np.array([[97, 98], [256, 99], [257, 257], [258, 100]], dtype=np.uint32)
+    for n in (1, 2047, 2048, 2049, 4097, 50_001):
+        ids = rng.integers(0, 260, n).astype(np.uint32)
+        assert engine.decode(ids, mm)[0] == oracle.decode(ids, mm), n
+
+
+def test_decode_on_device_round_trip(engine):
+    # train, then decode the resident stream and compare it with the resident shard without any host copy
+    data = corpus(0, 4_000_000, 3)
+    data = data[: len(data.tobytes().split(b"\0")[0])]
+    ctx = engine.Context(0)
+    try:
+        ctx.upload(data)
+        ctx.train(500)
+        m, t = ctx.download()
+        assert ctx.decode(m, download=False) == data.size
+        assert ctx.decode_mismatches() == 0
+        assert ctx.decode(m) == data.tobytes()
+        # encode with the learned table on the same context, decode again
+        ctx.encode(m)
+        assert ctx.decode(m, download=False) == data.size and ctx.decode_mismatches() == 0
+        # a wrong table must be noticed by the comparison
+        bad = m.copy()
+        bad[0] = bad[0][::-1] if bad[0][0] != bad[0][1] else [bad[0][0], bad[0][0] ^ 1]
+        assert ctx.decode(bad, download=False) == data.size
+        assert ctx.decode_mismatches() > 0
+    finally:
+        ctx.close()
