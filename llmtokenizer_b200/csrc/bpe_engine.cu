@@ -147,6 +147,8 @@ struct bpe_cuda_ctx
         u64 cap = 0;
     } arena[2];
     int arena_cur = 0;
+    int inplace = 1;              // RANGED passes compact the stream inside its own buffer (half the working set: late
+                                  // streams stay in the 126 MB L2 from pass to pass); BPE_CUDA_INPLACE=0 ping-pongs
     int l2_pin = 0;               // keep the pair table in L2 (access policy window); measured: no gain for apply/select and
                                   // 25 % slower passes on B200, so off (BPE_CUDA_L2_PIN=1 turns it on)
     size_t l2_window_max = 0, l2_persist_bytes = 0;
@@ -950,6 +952,9 @@ static int init_state(bpe_cuda_ctx *c, u64 n_local, u64 max_merges, bool encode,
     memset(&s, 0, sizeof s);
     s.tok[0] = c->d_tok_alloc[0] + 4;
     s.tok[1] = c->d_tok_alloc[1] + 4;
+    s.tok_real[0] = s.tok[0];
+    s.tok_real[1] = s.tok[1];
+    s.inplace = (u32)c->inplace;
     s.cur = 0;
     s.epoch = 1;
     s.n = n_local;
@@ -1358,6 +1363,8 @@ int bpe_cuda_ctx_create(int device, bpe_cuda_ctx_t **out)
     bpe_cuda_ctx *c = new bpe_cuda_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    if (const char *e = getenv("BPE_CUDA_INPLACE"))
+        c->inplace = atoi(e);
     if (const char *e = getenv("BPE_CUDA_L2_PIN"))
         c->l2_pin = atoi(e);
     if (c->l2_pin && prop.persistingL2CacheMaxSize > 0)
@@ -1619,6 +1626,8 @@ int bpe_cuda_ctx_set_option(bpe_cuda_ctx_t *c, const char *name, long long value
         c->batch_max = (int)value;
     else if (!strcmp(name, "ranges"))
         c->ranges_opt = (int)value;
+    else if (!strcmp(name, "inplace"))
+        c->inplace = (int)(value != 0);
     else if (!strcmp(name, "pdl"))
         c->pdl = (int)(value != 0);
     else if (!strcmp(name, "speculate"))

@@ -94,7 +94,8 @@ struct DevState
     u64 rcap;
     u32 *rcnt[2];
     u32 *redge[2];
-    u32 rp_done, pad_rp;
+    u32 rp_done, inplace; // inplace: a RANGED stream is compacted inside its own buffer (tok[0] == tok[1])
+    u32 *tok_real[2];     // the two allocations; tok[] aliases one of them while RANGED and in place
     // delta entries that became non-zero in the current pass (single GPU): apply walks this list instead of
     // scanning 4 * nb * V mostly-zero counters
     u32 *touched;

@@ -294,8 +294,11 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
     __shared__ u32 s_ba[BATCH_MAX], s_bb[BATCH_MAX];
     __shared__ __align__(16) u32 s_ab[2 * BATCH_MAX]; // the same pairs interleaved (a0, b0, a1, b1, ...)
 
-    const u32 *__restrict__ in = st->tok[ibuf] + (u64)cta * rcap;
-    u32 *__restrict__ out = st->tok[obuf] + (u64)cta * rcap;
+    // in and out are the same array when the stream is compacted in place (st->inplace): every tile is
+    // written at or below where it was read, and the storers wait for the next tile's load (whose front
+    // halo is the only part of it a store of this tile can reach) before they write
+    const u32 *in = st->tok[ibuf] + (u64)cta * rcap;
+    u32 *out = st->tok[obuf] + (u64)cta * rcap;
     const u32 ntiles = (n + V_TILE - 1) / V_TILE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int32_t *gdelta = delta + HDR_INTS;
@@ -568,6 +571,8 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
             const u32 s = t % NST;
             StageMeta &sm = s_meta[s];
             mbar_wait(&s_ready[s], (t / NST) & 1u);
+            if (t + 1 < ntiles)
+                mbar_wait(&s_full[(t + 1) % NST], ((t + 1) / NST) & 1u); // in place: see the note at `in`/`out`
             const u32 base = t * V_TILE;
             const u32 valid = (n - base < (u32)V_TILE) ? (n - base) : (u32)V_TILE;
             const bool full = (valid == (u32)V_TILE);
@@ -728,6 +733,8 @@ __global__ void __launch_bounds__(RANGE_MAX) partition_kernel(DevState *st)
         st->nr = nr;
         st->rcap = rcap;
         st->layout = LAYOUT_RANGED;
+        if (st->inplace)
+            st->tok[st->cur ^ 1u] = st->tok[st->cur]; // passes now read and write the same array
     }
 }
 
@@ -763,7 +770,7 @@ __global__ void __launch_bounds__(256) repack_kernel(DevState *st)
         }
         __syncthreads();
         const u32 *src = st->tok[st->cur] + (u64)c * st->rcap;
-        u32 *dst = st->tok[st->cur ^ 1u] + s_off;
+        u32 *dst = (st->tok_real[0] == st->tok[st->cur] ? st->tok_real[1] : st->tok_real[0]) + s_off;
         const u32 m = cnt[c];
         for (u32 i = threadIdx.x; i < m; i += blockDim.x)
             dst[i] = src[i];
@@ -775,6 +782,8 @@ __global__ void __launch_bounds__(256) repack_kernel(DevState *st)
         if (atomicAdd(&st->rp_done, 1u) == gridDim.x - 1)
         {
             st->rp_done = 0;
+            // every block has read its pointers (it counted itself in after copying): un-alias the buffers
+            st->tok[st->cur ^ 1u] = (st->tok_real[0] == st->tok[st->cur]) ? st->tok_real[1] : st->tok_real[0];
             st->cur ^= 1u;
             st->layout = LAYOUT_DENSE;
         }
