@@ -24,7 +24,11 @@ constexpr u64 EMPTY_KEY = ~0ull;
 constexpr u64 NO_SLOT = ~0ull;
 
 constexpr int MAX_RANKS = 8;
-constexpr int BATCH_MAX = 8; // merges per pass
+constexpr int BATCH_MAX = 8;
+// batched passes look tokens up in a byte table indexed by (token mod CLS_SIZE): the tokens of a batch must
+// differ mod CLS_SIZE (a stronger form of "pairwise different")
+constexpr u32 CLS_SIZE = 8192, CLS_MASK = CLS_SIZE - 1;
+__host__ __device__ inline bool tok_alias(u32 x, u32 y) { return ((x ^ y) & CLS_MASK) == 0; } // merges per pass
 constexpr int REC_INTS = 8;                    // one edge record
 constexpr int HDR_INTS = MAX_RANKS * REC_INTS; // edge records sit in front of the delta vectors
 
@@ -850,7 +854,7 @@ __device__ inline void decide_rank(DevState *st, const int32_t *delta_reduced)
             st->pause = PAUSE_SAME;
             st->stop = STOP_PAUSE;
         }
-        else if (a != b && st->batch_max > 1 && st->want_ranged && !st->static_mode && st->z >= st->batch_min_z &&
+        else if (!tok_alias(a, b) && st->batch_max > 1 && st->want_ranged && !st->static_mode && st->z >= st->batch_min_z &&
                  st->z >= st->hist_max)
         {
             // The following ranks can share this pass as long as nothing connects them: pairwise different tokens,
@@ -861,9 +865,10 @@ __device__ inline void decide_rank(DevState *st, const int32_t *delta_reduced)
             for (u64 r2 = r + 1; r2 < st->enc_total && st->nb < jcap; r2++)
             {
                 const u32 a2 = st->enc_merges[2 * r2], b2 = st->enc_merges[2 * r2 + 1];
-                bool ok = a2 != b2 && a2 < z_first && b2 < z_first;
+                bool ok = !tok_alias(a2, b2) && a2 < z_first && b2 < z_first;
                 for (u32 i = 0; ok && i < st->nb; i++)
-                    ok = a2 != st->ba[i] && a2 != st->bb[i] && b2 != st->ba[i] && b2 != st->bb[i];
+                    ok = !tok_alias(a2, st->ba[i]) && !tok_alias(a2, st->bb[i]) && !tok_alias(b2, st->ba[i]) &&
+                         !tok_alias(b2, st->bb[i]);
                 if (!ok)
                     break;
                 extend_batch(st, a2, b2);
@@ -1620,7 +1625,7 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
         t6 = gtime();
         // A committed a != b merge on a RANGED stream may take the next merges along in its pass.
         const bool extend = fits && st->stop == STOP_RUN && st->pending && st->batch_max > 1 && st->cand_T && st->want_ranged &&
-                            !st->static_mode && st->a != st->b && st->z >= st->batch_min_z && st->z >= st->hist_max &&
+                            !st->static_mode && !tok_alias(st->a, st->b) && st->z >= st->batch_min_z && st->z >= st->hist_max &&
                             st->merges_done < st->max_merges;
         s_win = extend ? s : NO_SLOT;
     }
@@ -1725,8 +1730,9 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
                 const u64 pay = s_wp[bl][wptr];
                 const u32 cnt = (u32)(bk >> 32), a = (u32)pay, b = (u32)(pay >> 32);
                 const bool overlap =
-                    __ballot_sync(0xFFFFFFFFu, (u32)lane < nacc && (a == my_a || a == my_b || b == my_a || b == my_b)) != 0;
-                const bool ok = !tie && cnt >= 2 && a != b && !overlap && r < jcap;
+                    __ballot_sync(0xFFFFFFFFu, (u32)lane < nacc && (tok_alias(a, my_a) || tok_alias(a, my_b) || tok_alias(b, my_a) ||
+                                                                    tok_alias(b, my_b))) != 0;
+                const bool ok = !tie && cnt >= 2 && !tok_alias(a, b) && !overlap && r < jcap;
                 if (!ok)
                 {
                     bound = cnt;

@@ -63,7 +63,7 @@ constexpr int V_WARP_OFFSETS = V_WARP_PRODUCER + 1;
 __host__ __device__ inline size_t stream_smem_bytes(bool hist, u32 z)
 {
     return (size_t)(hist ? V_STAGES_HIST : V_STAGES) * V_TILE_BYTES + (size_t)V_STORE_WARPS * V_STAGING_WORDS * 4 +
-           (hist ? 16 * ((size_t)z + 1) : 0);
+           (hist ? 16 * ((size_t)z + 1) : (size_t)CLS_SIZE);
 }
 
 // ---- mbarrier / bulk-copy wrappers (PTX ISA: mbarrier, cp.async.bulk) --------------------------
@@ -179,56 +179,49 @@ __device__ __forceinline__ u32 pair_of(u32 x, u32 y, u32 nb, const u32 *ba, cons
             r = i + 1;
     return r;
 }
-// as iter_bits; mi = four nibbles, 1 + index of the pair whose replacement starts on token k.  The pairs are read
-// from shared memory (broadcast loads; registers are better spent elsewhere); a thread first asks whether any of
-// its four tokens is the first token of ANY pair (one compare per token and pair) and only then looks for the pair.
-__device__ __forceinline__ bool iter_bits_multi(const u32 *sin, int j, int lane, u32 nb, const u32 *ra, u32 valid, bool full,
-                                                const uint4 &c, u32 &bits, u32 &v, u32 &mi)
+// as iter_bits; mi = four nibbles, 1 + index of the pair whose replacement starts on token k.  Which pair a
+// token belongs to comes from a byte table in shared memory indexed by (token mod CLS_SIZE): low nibble = 1 +
+// index of the pair it is the FIRST token of, high nibble = the pair it is the SECOND token of (the tokens of a
+// batch are pairwise different mod CLS_SIZE, see tok_alias).  A replacement starts where the low nibble of a
+// token equals the high nibble of the next one and is not zero: the cost does not grow with the batch.  Ids
+// beyond CLS_SIZE alias table entries, so candidates are then checked against the real pair (verify).
+__device__ __forceinline__ bool iter_bits_multi(const u32 *sin, int j, int lane, const unsigned char *cls, bool verify,
+                                                const u32 *ra, u32 valid, bool full, const uint4 &c, u32 &bits, u32 &v, u32 &mi)
 {
+    const u32 k0 = cls[c.x & CLS_MASK], k1 = cls[c.y & CLS_MASK], k2 = cls[c.z & CLS_MASK], k3 = cls[c.w & CLS_MASK];
     const u32 nxl = sin[(j + 1) * 128];
     const u32 pvl = sin[j * 128 - 1];
-    u32 nx = __shfl_down_sync(0xFFFFFFFFu, c.x, 1);
+    u32 kn = __shfl_down_sync(0xFFFFFFFFu, k0, 1);
     if (lane == 31)
-        nx = nxl;
-    const u32 x0 = __shfl_sync(0xFFFFFFFFu, c.x, 0);
-    // two pairs per 128-bit broadcast load: (a0, b0, a1, b1); unused entries hold SENT, which no token equals
-    const uint4 *p4 = reinterpret_cast<const uint4 *>(ra);
-    bool hit = false, carry_hit = false;
-#pragma unroll
-    for (int q = 0; q < BATCH_MAX / 2; q++)
-        if ((u32)(2 * q) < nb)
-        {
-            const uint4 t = p4[q];
-            hit = hit || c.x == t.x || c.y == t.x || c.z == t.x || c.w == t.x || c.x == t.z || c.y == t.z || c.z == t.z || c.w == t.z;
-            carry_hit = carry_hit || (pvl == t.x && x0 == t.y) || (pvl == t.z && x0 == t.w);
-        }
-    mi = 0;
-    if (hit)
+        kn = cls[nxl & CLS_MASK];
+    const u32 kx0 = __shfl_sync(0xFFFFFFFFu, k0, 0);
+    const u32 kp = cls[pvl & CLS_MASK];
+    u32 carry = ((kp & 15u) == (kx0 >> 4)) ? (kp & 15u) : 0u;
+    const u32 m0 = ((k0 & 15u) == (k1 >> 4)) ? (k0 & 15u) : 0u;
+    const u32 m1 = ((k1 & 15u) == (k2 >> 4)) ? (k1 & 15u) : 0u;
+    const u32 m2 = ((k2 & 15u) == (k3 >> 4)) ? (k2 & 15u) : 0u;
+    const u32 m3 = ((k3 & 15u) == (kn >> 4)) ? (k3 & 15u) : 0u;
+    mi = m0 | (m1 << 4) | (m2 << 8) | (m3 << 12);
+    if (verify) // uniform: the vocabulary is larger than the table
     {
+        u32 nx = __shfl_down_sync(0xFFFFFFFFu, c.x, 1);
+        if (lane == 31)
+            nx = nxl;
+        const u32 x0 = __shfl_sync(0xFFFFFFFFu, c.x, 0);
+        if (mi)
+        {
+            const u32 tk[5] = {c.x, c.y, c.z, c.w, nx};
 #pragma unroll
-        for (int q = 0; q < BATCH_MAX / 2; q++)
-            if ((u32)(2 * q) < nb)
+            for (int k = 0; k < 4; k++)
             {
-                const uint4 t = p4[q];
-                if (c.x == t.x && c.y == t.y)
-                    mi |= (2 * q + 1);
-                if (c.y == t.x && c.z == t.y)
-                    mi |= (2 * q + 1) << 4;
-                if (c.z == t.x && c.w == t.y)
-                    mi |= (2 * q + 1) << 8;
-                if (c.w == t.x && nx == t.y)
-                    mi |= (2 * q + 1) << 12;
-                if (c.x == t.z && c.y == t.w)
-                    mi |= (2 * q + 2);
-                if (c.y == t.z && c.z == t.w)
-                    mi |= (2 * q + 2) << 4;
-                if (c.z == t.z && c.w == t.w)
-                    mi |= (2 * q + 2) << 8;
-                if (c.w == t.z && nx == t.w)
-                    mi |= (2 * q + 2) << 12;
+                const u32 m = (mi >> (4 * k)) & 15u;
+                if (m && (tk[k] != ra[2 * (m - 1)] || tk[k + 1] != ra[2 * (m - 1) + 1]))
+                    mi &= ~(15u << (4 * k));
             }
+        }
+        if (carry && (pvl != ra[2 * (carry - 1)] || x0 != ra[2 * (carry - 1) + 1]))
+            carry = 0;
     }
-    const u32 carry = carry_hit ? 1u : 0u;
     v = 4;
     if (!full)
     {
@@ -239,9 +232,9 @@ __device__ __forceinline__ bool iter_bits_multi(const u32 *sin, int j, int lane,
     bits = 0;
     if (!(__any_sync(0xFFFFFFFFu, mi != 0) || carry || !full))
         return false;
-    const bool m3 = (mi >> 12) != 0;
-    const u32 mb3 = __ballot_sync(0xFFFFFFFFu, m3);
-    const u32 r0 = (((mb3 << 1) | carry) >> lane) & 1u;
+    const bool b3 = (mi >> 12) != 0;
+    const u32 mb3 = __ballot_sync(0xFFFFFFFFu, b3);
+    const u32 r0 = (((mb3 << 1) | (carry ? 1u : 0u)) >> lane) & 1u;
     bits = ((mi & 0xFu) ? 1u : 0u) | ((mi & 0xF0u) ? 2u : 0u) | ((mi & 0xF00u) ? 4u : 0u) | ((mi & 0xF000u) ? 8u : 0u) | (r0 << 4);
     return true;
 }
@@ -288,6 +281,8 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
     u32 *s_in = smem;                                       // NST x V_STAGE_WORDS
     u32 *s_staging = smem + NST * V_STAGE_WORDS;       // V_STORE_WARPS x V_STAGING_WORDS
     int32_t *s_hist = reinterpret_cast<int32_t *>(s_staging + V_STORE_WARPS * V_STAGING_WORDS);
+    unsigned char *s_cls = reinterpret_cast<unsigned char *>(s_hist); // <false> only: token -> pair table of a batched pass
+    const bool cls_verify = (z + nb > CLS_SIZE);
     __shared__ __align__(8) u64 s_full[NST], s_scanned[NST], s_ready[NST], s_empty[NST], s_halo_ready;
     __shared__ StageMeta s_meta[NST];
     __shared__ u32 s_halo[5]; // tokens at range positions -2, -1, n, n+1, n+2
@@ -327,7 +322,20 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
         s_ab[2 * tid] = s_ba[tid];
         s_ab[2 * tid + 1] = s_bb[tid];
     }
+    if (!SMEM_HIST && nb > 1)
+        for (u32 i = tid; i < CLS_SIZE / 4; i += V_THREADS)
+            reinterpret_cast<u32 *>(s_cls)[i] = 0;
     __syncthreads();
+    if (!SMEM_HIST && nb > 1)
+    {
+        // every byte has one writer: the tokens of a batch differ mod CLS_SIZE (tok_alias in the selection)
+        if (tid < (int)nb)
+        {
+            s_cls[s_ba[tid] & CLS_MASK] = (unsigned char)(tid + 1);
+            s_cls[s_bb[tid] & CLS_MASK] = (unsigned char)((tid + 1) << 4);
+        }
+        __syncthreads();
+    }
 
     if (warp == V_WARP_PRODUCER)
     {
@@ -459,7 +467,7 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
                 const uint4 c = *reinterpret_cast<const uint4 *>(sin + j * 128 + lane * 4);
                 u32 bits, v, mi = 0, ktj = 128;
                 const bool slow_it = (nb == 1) ? iter_bits(sin, j, lane, a, b, valid, full, c, bits, v)
-                                               : iter_bits_multi(sin, j, lane, nb, s_ab, valid, full, c, bits, v, mi);
+                                               : iter_bits_multi(sin, j, lane, s_cls, cls_verify, s_ab, valid, full, c, bits, v, mi);
                 if (slow_it)
                 {
                     slow |= 1u << j;
@@ -643,7 +651,7 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
                         v = full ? 4u : ((p >= valid) ? 0u : ((valid - p < 4u) ? (valid - p) : 4u));
                     }
                     else
-                        iter_bits_multi(sin, j, lane, nb, s_ab, valid, full, c, bits, v, mi);
+                        iter_bits_multi(sin, j, lane, s_cls, cls_verify, s_ab, valid, full, c, bits, v, mi);
                     const u32 keep = keep_mask(bits, v);
                     const u32 kc = (u32)__popc(keep);
                     // exclusive prefix of the kept counts (0..4 each) from three ballots

@@ -135,6 +135,34 @@ def test_batched_passes_long_runs(engine, oracle):
         assert np.array_equal(ids2, oracle.encode(other, m))
 
 
+def test_batched_passes_beyond_the_class_table(engine, oracle):
+    """Batched passes find a token's pair through an 8,192-entry table indexed by (id mod 8192): once ids
+    pass 8,192 they alias table entries, candidates are checked against the real pair, and pairs whose tokens
+    alias each other may not share a pass.  10,000 merges on a stream that stays above 1,048,576 tokens;
+    the unbatched engine (itself pinned to the oracle by the tests above) is the checker, the oracle checks
+    the encoder on a smaller text and the decoder closes the loop."""
+    data = corpus(0, 12_000_000, 11)
+    cap = 10_000
+    res = []
+    for bm in (8, 1):
+        ctx = engine.Context(0)
+        ctx.set_option("batch_max", bm)
+        ctx.upload(data)
+        st = ctx.train(cap)
+        m, t = ctx.download()
+        if bm == 8:
+            assert st["batch_merges"] > 0 and ctx.decode(m, download=False) == data.size and ctx.decode_mismatches() == 0
+        ctx.close()
+        res.append((m, t, st))
+    (m, t, st), (m1, t1, s1) = res
+    assert len(m) == cap and s1["batch_merges"] == 0
+    assert np.array_equal(m, m1) and np.array_equal(t, t1), st
+    ids, se = engine.encode(data, m)
+    assert np.array_equal(ids, t) and se["batch_merges"] > 0, se
+    other = corpus(0, 400_000, 12)
+    assert np.array_equal(engine.encode(other, m)[0], oracle.encode(other, m))
+
+
 def test_batched_passes_with_many_ties(engine, oracle):
     """Nearly uniform symbols: late merges all have almost the same count, so the order inside and between
     batches is decided by the bucket order again and again (and now and then by a same-bucket tie, which
