@@ -769,6 +769,111 @@ __device__ inline void extend_batch(DevState *st, u32 a, u32 b)
 
 constexpr int SEL_THREADS = 512;
 
+// What the batch extension needs to know about the merge decide_list() has just committed (shared memory)
+struct Committed
+{
+    u32 ok;             // a merge was committed and the pass may take more merges along
+    u32 a, b, freq, z;  // the committed merge
+    u32 cand_T, batch_max, hist_max, hist_words;
+    u64 merges_done;    // after the commit
+    u64 max_merges;
+    u64 bt0;            // worker-table buckets after the commit
+    u32 *merges;
+    u64 *n_hist;
+};
+
+// decide() for the list mode on one GPU (the per-pass critical path): the same decisions, but every
+// field is loaded up front in one burst (the loads overlap; in decide()/commit_merge() each load waits for the
+// stores in front of it, five serial round trips to L2) and the merge is committed from registers.
+__device__ inline void decide_list(DevState *st, u64 k, u64 s, u32 m, const PreDecide *pre, Committed *out)
+{
+    const u64 D = (u64)st->distinct, md = st->merges_done, mm = st->max_merges, n_local = st->n, bt0 = st->bt[0];
+    const u32 cand_T = st->cand_T, stat = st->static_mode, wr = st->want_ranged, epoch = st->epoch;
+    const u32 batch_max = st->batch_max, batch_min_z = st->batch_min_z, hist_max = st->hist_max, hist_words = st->hist_words;
+    u32 *merges = st->merges;
+    u64 *n_hist = st->n_hist;
+    const u64 key = (s != NO_SLOT) ? __ldcg(st->tkey + s) : 0ull;
+    out->ok = 0;
+    st->sel_key = k;
+    st->sel_slot = s;
+    st->sel_mult = m;
+    st->n_global = n_local;
+    const u32 freq = (u32)(k >> 32);
+    if (cand_T && D != 0 && freq < cand_T && md < mm)
+    {
+        st->pause = PAUSE_REBUILD; // see decide()
+        st->stop = STOP_PAUSE;
+        return;
+    }
+    if (D == 0 || m == 0 || freq <= 1 || md >= mm) // bpe.c:730, bpe.c:745, cap
+    {
+        st->stop = STOP_DONE;
+        return;
+    }
+    if (!stat && n_local < STATIC_LIMIT)
+    {
+        st->static_mode = 1;
+        st->pause = PAUSE_STATIC;
+        st->stop = STOP_PAUSE;
+        return;
+    }
+    const bool tie = (m > 1), edge = pre->edge != 0;
+    if (tie || edge)
+    {
+        if (tie)
+            st->same_bucket_ties++;
+        if (edge)
+            st->threshold_edges++;
+        st->pause = (tie ? PAUSE_TIE : 0u) | (edge ? PAUSE_EDGE : 0u);
+        st->stop = STOP_PAUSE;
+        return;
+    }
+    // commit_merge(), from registers
+    const u32 a = (u32)(key & 0xFFFFFFFFull), b = (u32)(key >> 32), z = (u32)(256 + md);
+    st->a = a;
+    st->b = b;
+    st->z = z;
+    st->freq = freq;
+    st->skip = 0;
+    st->nb = 1;
+    st->ba[0] = a;
+    st->bb[0] = b;
+    merges[2 * md] = a;
+    merges[2 * md + 1] = b;
+    u64 bt_new = bt0;
+    if (n_local >= STATIC_LIMIT)
+    {
+        bt_new = grown_buckets(bt0, D, pre->last_new != 0);
+        st->bt[0] = bt_new;
+    }
+    st->n_next = 0;
+    st->pending = 1;
+    n_hist[md] = n_local;
+    st->merges_done = md + 1;
+    st->epoch = epoch + 1;
+    st->ticket = 0;
+    if (a == b && wr && !stat)
+    {
+        st->pause = PAUSE_SAME; // see decide()
+        st->stop = STOP_PAUSE;
+        return;
+    }
+    out->ok = (batch_max > 1 && cand_T && wr && !stat && !tok_alias(a, b) && z >= batch_min_z && z >= hist_max && md + 1 < mm) ? 1u : 0u;
+    out->a = a;
+    out->b = b;
+    out->freq = freq;
+    out->z = z;
+    out->cand_T = cand_T;
+    out->batch_max = batch_max;
+    out->hist_max = hist_max;
+    out->hist_words = hist_words;
+    out->merges_done = md + 1;
+    out->max_merges = mm;
+    out->bt0 = bt_new;
+    out->merges = merges;
+    out->n_hist = n_hist;
+}
+
 // The decision once the best packed key (count << 32 | ~bucket), its multiplicity and a slot holding
 // it are known: stop / pause / commit (bpe.c:730-758).  One thread.
 __device__ inline void decide(DevState *st, u64 k, u64 s, u32 m, const int32_t *delta_reduced, const PreDecide *pre = nullptr)
@@ -1617,16 +1722,41 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
     const u64 t4 = gtime();
     sel_block_reduce(k, s, m, sm); // (its barriers also publish s_pre)
     __shared__ u64 s_win;          // slot of the pair chosen last (NO_SLOT: stop extending the batch)
+    __shared__ Committed s_cm;
     u64 t5 = 0, t6 = 0;
     if (threadIdx.x == 0)
     {
         t5 = gtime();
-        decide(st, k, s, m, delta_in, &s_pre);
+        bool extend = false;
+        if (st->world == 1 && s_pre.valid)
+        {
+            decide_list(st, k, s, m, &s_pre, &s_cm);
+            extend = fits && s_cm.ok;
+        }
+        else
+        {
+            decide(st, k, s, m, delta_in, &s_pre); // several GPUs: the general form
+            extend = fits && st->stop == STOP_RUN && st->pending && st->batch_max > 1 && st->cand_T && st->want_ranged &&
+                     !st->static_mode && !tok_alias(st->a, st->b) && st->z >= st->batch_min_z && st->z >= st->hist_max &&
+                     st->merges_done < st->max_merges;
+            if (extend)
+            {
+                s_cm.a = st->a;
+                s_cm.b = st->b;
+                s_cm.freq = st->freq;
+                s_cm.z = st->z;
+                s_cm.cand_T = st->cand_T;
+                s_cm.batch_max = st->batch_max;
+                s_cm.hist_max = st->hist_max;
+                s_cm.hist_words = st->hist_words;
+                s_cm.merges_done = st->merges_done;
+                s_cm.max_merges = st->max_merges;
+                s_cm.bt0 = st->bt[0];
+                s_cm.merges = st->merges;
+                s_cm.n_hist = st->n_hist;
+            }
+        }
         t6 = gtime();
-        // A committed a != b merge on a RANGED stream may take the next merges along in its pass.
-        const bool extend = fits && st->stop == STOP_RUN && st->pending && st->batch_max > 1 && st->cand_T && st->want_ranged &&
-                            !st->static_mode && !tok_alias(st->a, st->b) && st->z >= st->batch_min_z && st->z >= st->hist_max &&
-                            st->merges_done < st->max_merges;
         s_win = extend ? s : NO_SLOT;
     }
     __syncthreads();
@@ -1688,16 +1818,17 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
         __syncthreads();
         if (warp == 0)
         {
-            const u64 room = st->max_merges - st->merges_done + 1; // merges the cap still allows, this pass included
-            u32 jcap = (u32)min((u64)min(st->batch_max, (u32)BATCH_MAX), room);
+            const Committed cm = s_cm; // (one burst of shared-memory loads)
+            const u64 room = cm.max_merges - cm.merges_done + 1; // merges the cap still allows, this pass included
+            u32 jcap = (u32)min((u64)min(cm.batch_max, (u32)BATCH_MAX), room);
             // while replacements are frequent their deltas are privatised in shared memory: keep the batch small
             // enough for that histogram (one block of 4 vectors per merge) until the ids outgrow it
             // (beyond hist_max ids a pass makes few enough replacements for global atomics)
-            if (st->z < st->hist_max)
-                while (jcap > 1 && jcap * 4 * (st->z + jcap) > st->hist_words)
+            if (cm.z < cm.hist_max)
+                while (jcap > 1 && jcap * 4 * (cm.z + jcap) > cm.hist_words)
                     jcap--;
             // lane i keeps accepted pair i; lane w < NW walks warp w's list
-            u32 my_a = (lane == 0) ? st->a : SENT, my_b = (lane == 0) ? st->b : SENT, my_c = (lane == 0) ? st->freq : 0u;
+            u32 my_a = (lane == 0) ? cm.a : SENT, my_b = (lane == 0) ? cm.b : SENT, my_c = (lane == 0) ? cm.freq : 0u;
             u32 nacc = 1, bound = 0, ptr = 0;
             bool stop = false;
             for (u32 r = 1; r <= jcap && !stop; r++)
@@ -1716,11 +1847,11 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
                         bl = l2;
                     }
                 }
-                if (bk == 0 || (u32)(bk >> 32) < st->cand_T)
+                if (bk == 0 || (u32)(bk >> 32) < cm.cand_T)
                 {
                     // The list is only complete for counts >= cand_T: entries that have decayed below the threshold
                     // say nothing about the pairs that were never listed.  Everything else is below the threshold.
-                    bound = st->cand_T - 1;
+                    bound = cm.cand_T - 1;
                     break;
                 }
                 // same-bucket tie: another list's head, or the winner list's next entry, has the same packed key
@@ -1760,7 +1891,7 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
             // How far can D move inside the batch?  A merge changes at most four pair instances per replacement,
             // and at most one key per delta counter (four per token id).
             u64 dm = 0;
-            const u64 per_tok = 4ull * (st->z + BATCH_MAX + 1);
+            const u64 per_tok = 4ull * (cm.z + BATCH_MAX + 1);
             for (u32 i = 0; i < nacc; i++)
                 dm += min(4ull * __shfl_sync(0xFFFFFFFFu, my_c, i), per_tok);
             // the merged table is rebuilt from 65,536 buckets every iteration: no doubling threshold may lie
@@ -1773,16 +1904,25 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
                 if (thr > D + dm)
                     break;
             }
-            if (nacc > 1 && D + dm >= resize_threshold(st->bt[0]))
+            if (nacc > 1 && D + dm >= resize_threshold(cm.bt0))
                 nacc = 1;
-            for (u32 i = 1; i < nacc; i++)
+            // extend_batch() for merges 1 .. nacc-1, every lane its own merge, nothing read back
+            if (lane >= 1 && (u32)lane < nacc)
             {
-                const u32 a = __shfl_sync(0xFFFFFFFFu, my_a, i), b = __shfl_sync(0xFFFFFFFFu, my_b, i);
-                if (lane == 0)
-                    extend_batch(st, a, b);
+                const u64 km = cm.merges_done + (u32)lane - 1;
+                st->ba[lane] = my_a;
+                st->bb[lane] = my_b;
+                cm.merges[2 * km] = my_a;
+                cm.merges[2 * km + 1] = my_b;
+                cm.n_hist[km] = ~0ull; // rides along: no pass of its own
             }
             if (lane == 0 && nacc > 1)
-                st->batch_passes++;
+            {
+                st->nb = nacc;
+                st->merges_done = cm.merges_done + nacc - 1;
+                atomicAdd(reinterpret_cast<unsigned long long *>(&st->batch_merges), (unsigned long long)(nacc - 1));
+                atomicAdd(reinterpret_cast<unsigned long long *>(&st->batch_passes), 1ull);
+            }
         }
     }
     if (threadIdx.x == 0)
