@@ -1161,6 +1161,10 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
                 h->dbg[6], (double)h->dbg[0] / h->dbg[6], (double)h->dbg[1] / h->dbg[6], (double)h->dbg[2] / h->dbg[6],
                 (double)h->dbg[3] / h->dbg[6], (double)h->dbg[4] / h->dbg[6], (double)h->dbg[5] / h->dbg[6],
                 (double)h->dbg[7] / h->dbg[6]);
+    if (getenv("BPE_CUDA_DEBUG"))
+        fprintf(stderr, "[bpe_cuda] batch walks ended by: cap %llu | below cand_T %llu | tie %llu | overlap %llu | a==b/alias %llu | list used up %llu | merges trimmed by the bound %llu, by the D margin %llu\n",
+                (unsigned long long)h->ext_why[0], (unsigned long long)h->ext_why[1], (unsigned long long)h->ext_why[2],
+                (unsigned long long)h->ext_why[3], (unsigned long long)h->ext_why[4], (unsigned long long)h->ext_why[5], (unsigned long long)h->ext_why[6], (unsigned long long)h->ext_why[7]);
     c->res_n_merges = (size_t)h->merges_done;
     c->res_n_tokens = (size_t)h->n;
     c->stats.n_merges = h->merges_done;

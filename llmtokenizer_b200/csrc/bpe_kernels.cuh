@@ -100,6 +100,7 @@ struct DevState
     u32 *redge[2];
     u32 rp_done, inplace; // inplace: a RANGED stream is compacted inside its own buffer (tok[0] == tok[1])
     u32 *tok_real[2];     // the two allocations; tok[] aliases one of them while RANGED and in place
+    u64 ext_why[8];       // debug statistics: why batch extensions ended (see apply_select_kernel)
     // delta entries that became non-zero in the current pass (single GPU): apply walks this list instead of
     // scanning 4 * nb * V mostly-zero counters
     u32 *touched;
@@ -1829,7 +1830,7 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
                     jcap--;
             // lane i keeps accepted pair i; lane w < NW walks warp w's list
             u32 my_a = (lane == 0) ? cm.a : SENT, my_b = (lane == 0) ? cm.b : SENT, my_c = (lane == 0) ? cm.freq : 0u;
-            u32 nacc = 1, bound = 0, ptr = 0;
+            u32 nacc = 1, bound = 0, ptr = 0, why = 0; // why: 0 cap, 1 below cand_T, 2 tie, 3 overlap, 4 a==b/alias/cnt<2, 5 list used up
             bool stop = false;
             for (u32 r = 1; r <= jcap && !stop; r++)
             {
@@ -1852,6 +1853,7 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
                     // The list is only complete for counts >= cand_T: entries that have decayed below the threshold
                     // say nothing about the pairs that were never listed.  Everything else is below the threshold.
                     bound = cm.cand_T - 1;
+                    why = 1;
                     break;
                 }
                 // same-bucket tie: another list's head, or the winner list's next entry, has the same packed key
@@ -1867,6 +1869,7 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
                 if (!ok)
                 {
                     bound = cnt;
+                    why = tie ? 2u : (overlap ? 3u : (r >= jcap ? 0u : 4u));
                     break;
                 }
                 if ((u32)lane == nacc)
@@ -1883,29 +1886,53 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
                 {
                     bound = cnt;
                     stop = true;
+                    why = 5;
                 }
             }
+            const u32 nacc_walk = nacc; // accepted before the bound / margin rules trim the batch
             // strictly above the bound; D may move by at most 4 pair instances per replacement
             while (nacc > 1 && __shfl_sync(0xFFFFFFFFu, my_c, nacc - 1) <= bound)
                 nacc--;
-            // How far can D move inside the batch?  A merge changes at most four pair instances per replacement,
-            // and at most one key per delta counter (four per token id).
-            u64 dm = 0;
-            const u64 per_tok = 4ull * (cm.z + BATCH_MAX + 1);
-            for (u32 i = 0; i < nacc; i++)
-                dm += min(4ull * __shfl_sync(0xFFFFFFFFu, my_c, i), per_tok);
-            // the merged table is rebuilt from 65,536 buckets every iteration: no doubling threshold may lie
-            // within reach on either side; the worker table only ever grows: its next threshold must be out of reach
-            for (u64 bsz = 65536; nacc > 1 && bsz <= (1ull << 40); bsz *= 2)
+            const u32 nacc_bound = nacc;
+            // How far can D move before merge i of the batch is selected (i.e. through merges 0 .. i-1)?  A merge
+            // with c replacements creates at most min(2c, 2V) new keys ((x,z) and (z,y), one of each per
+            // replacement, V token ids) and empties at most that many old ones ((x,a), (b,y)) plus (a,b) itself.
+            // The merged table is rebuilt from 65,536 buckets every iteration: no doubling threshold may lie within
+            // reach on either side (so B(D), the exact-threshold edge and the tie-break order stay what this walk
+            // assumed); the worker table only ever grows: its next threshold must stay out of reach.  The batch is
+            // cut in front of the first merge for which that cannot be promised.
+            const u64 vb = 2ull * (cm.z + BATCH_MAX);
+            const u64 mine = ((u32)lane < nacc) ? min(2ull * my_c, vb) : 0ull;
+            u64 up = mine, down = mine + (((u32)lane < nacc) ? 1ull : 0ull); // inclusive prefix sums below
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
             {
-                const u64 thr = resize_threshold(bsz);
-                if (thr + dm >= D && thr <= D + dm)
-                    nacc = 1;
-                if (thr > D + dm)
-                    break;
+                const u64 u2 = __shfl_up_sync(0xFFFFFFFFu, up, o), d2 = __shfl_up_sync(0xFFFFFFFFu, down, o);
+                if (lane >= o)
+                {
+                    up += u2;
+                    down += d2;
+                }
             }
-            if (nacc > 1 && D + dm >= resize_threshold(cm.bt0))
-                nacc = 1;
+            up = __shfl_up_sync(0xFFFFFFFFu, up, 1); // merges 0 .. lane-1
+            down = __shfl_up_sync(0xFFFFFFFFu, down, 1);
+            bool clear = true;
+            if (lane >= 1 && (u32)lane < nacc)
+            {
+                for (u64 bsz = 65536; bsz <= (1ull << 40); bsz *= 2)
+                {
+                    const u64 thr = resize_threshold(bsz);
+                    if (thr + down >= D && thr <= D + up)
+                        clear = false;
+                    if (thr > D + up)
+                        break;
+                }
+                if (D + up + 1 >= resize_threshold(cm.bt0))
+                    clear = false;
+            }
+            const u32 blocked = __ballot_sync(0xFFFFFFFFu, !clear);
+            if (blocked)
+                nacc = min(nacc, (u32)__ffs(blocked) - 1u);
             // extend_batch() for merges 1 .. nacc-1, every lane its own merge, nothing read back
             if (lane >= 1 && (u32)lane < nacc)
             {
@@ -1915,6 +1942,15 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
                 cm.merges[2 * km] = my_a;
                 cm.merges[2 * km + 1] = my_b;
                 cm.n_hist[km] = ~0ull; // rides along: no pass of its own
+            }
+            if (lane == 0)
+            {
+                // 0-5: why the walk ended; 6: merges lost to the strictly-above-the-bound rule; 7: to the D margin
+                atomicAdd(reinterpret_cast<unsigned long long *>(&st->ext_why[why]), 1ull);
+                if (nacc_walk > nacc_bound)
+                    atomicAdd(reinterpret_cast<unsigned long long *>(&st->ext_why[6]), (unsigned long long)(nacc_walk - nacc_bound));
+                if (nacc_bound > nacc)
+                    atomicAdd(reinterpret_cast<unsigned long long *>(&st->ext_why[7]), (unsigned long long)(nacc_bound - nacc));
             }
             if (lane == 0 && nacc > 1)
             {

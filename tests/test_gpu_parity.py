@@ -223,6 +223,9 @@ def test_sharded_training_and_encoding_match_oracle(engine, oracle, P):
         pytest.skip(f"needs {P} GPUs")
     assert_same(engine, oracle, corpus(0, 8_000_000, 7), cap=200, n_gpus=P, what=f"zipf_ascii 8 MB P={P}")
     assert_same(engine, oracle, corpus(1, 6_000_000, 8), cap=100, n_gpus=P, what=f"zipf_bytes 6 MB P={P}")
+    # long enough for merges to share passes (ids beyond the shared-memory histogram), all ranks deciding alike
+    _, _, st = assert_same(engine, oracle, corpus(0, 12_000_000, 71), cap=1300, n_gpus=P, what=f"zipf_ascii 12 MB P={P}")
+    assert st["batch_merges"] > 0, st
     # long runs of equal bytes: a == b merges whose run parity crosses shard boundaries
     rng = np.random.default_rng(P)
     runs = np.repeat(rng.integers(97, 100, 400_000, dtype=np.uint8), rng.integers(1, 30, 400_000))[:4_000_001]
