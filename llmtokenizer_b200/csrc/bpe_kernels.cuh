@@ -1817,9 +1817,12 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
             }
         }
         __syncthreads();
+        __shared__ u32 s_acc_a[BATCH_MAX], s_acc_b[BATCH_MAX];
+        __shared__ u32 s_resc[4]; // bound, merges the walk accepted, merges strictly above the bound, rescue result
+        const Committed cm = s_cm; // (one burst of shared-memory loads)
+        u32 my_a = SENT, my_b = SENT, my_c = 0, nacc = 1, bound = 0, why = 0, nacc_walk = 1, nacc_bound = 1;
         if (warp == 0)
         {
-            const Committed cm = s_cm; // (one burst of shared-memory loads)
             const u64 room = cm.max_merges - cm.merges_done + 1; // merges the cap still allows, this pass included
             u32 jcap = (u32)min((u64)min(cm.batch_max, (u32)BATCH_MAX), room);
             // while replacements are frequent their deltas are privatised in shared memory: keep the batch small
@@ -1829,8 +1832,13 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
                 while (jcap > 1 && jcap * 4 * (cm.z + jcap) > cm.hist_words)
                     jcap--;
             // lane i keeps accepted pair i; lane w < NW walks warp w's list
-            u32 my_a = (lane == 0) ? cm.a : SENT, my_b = (lane == 0) ? cm.b : SENT, my_c = (lane == 0) ? cm.freq : 0u;
-            u32 nacc = 1, bound = 0, ptr = 0, why = 0; // why: 0 cap, 1 below cand_T, 2 tie, 3 overlap, 4 a==b/alias/cnt<2, 5 list used up
+            if (lane == 0)
+            {
+                my_a = cm.a;
+                my_b = cm.b;
+                my_c = cm.freq;
+            }
+            u32 ptr = 0; // why: 0 cap, 1 below cand_T, 2 tie, 3 overlap, 4 a==b/alias/cnt<2, 5 list used up
             bool stop = false;
             for (u32 r = 1; r <= jcap && !stop; r++)
             {
@@ -1889,11 +1897,73 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
                     why = 5;
                 }
             }
-            const u32 nacc_walk = nacc; // accepted before the bound / margin rules trim the batch
-            // strictly above the bound; D may move by at most 4 pair instances per replacement
+            nacc_walk = nacc; // accepted before the bound / margin rules trim the batch
+            // Strictly above the bound: every pair whose count the accepted merges can change, or that they create,
+            // ranks at or below the first candidate that was not accepted (count `bound`).
             while (nacc > 1 && __shfl_sync(0xFFFFFFFFu, my_c, nacc - 1) <= bound)
                 nacc--;
-            const u32 nacc_bound = nacc;
+            if ((u32)lane < (u32)BATCH_MAX)
+            {
+                s_acc_a[lane] = ((u32)lane < nacc_walk) ? my_a : SENT;
+                s_acc_b[lane] = ((u32)lane < nacc_walk) ? my_b : SENT;
+            }
+            if (lane == 0)
+            {
+                s_resc[0] = bound;
+                s_resc[1] = nacc_walk;
+                s_resc[2] = (why == 0 || why == 3 || why == 4) ? nacc : nacc_walk; // (no rescue after a tie / a used-up list)
+                s_resc[3] = 0xFFFFFFFFu;
+            }
+        }
+        __syncthreads();
+        if (s_resc[2] < s_resc[1])
+        {
+            // Accepted merges whose count EQUALS the bound: merge i is still certain to be next unless a pair with
+            // exactly that count contains a token of the merges in front of it (only such a pair can turn into a new
+            // pair (x, z_j) of the same count that the bucket order might put first).  Every pair with that count is
+            // in the list (bound >= cand_T here): each thread looks at its own candidates, and the first threads at
+            // the entries that were moved to the warps' lists.  Result: the smallest merge index any of them touches.
+            const u32 bnd = s_resc[0], nw = s_resc[1];
+            u32 jm = 0xFFFFFFFFu;
+            auto look = [&](u64 key, u64 pair) {
+                if ((u32)(key >> 32) != bnd)
+                    return;
+                const u32 a = (u32)pair, b = (u32)(pair >> 32);
+                for (u32 i = 0; i < nw; i++)
+                {
+                    const u32 xa = s_acc_a[i], xb = s_acc_b[i];
+                    if (a == xa && b == xb)
+                        return; // an accepted merge itself
+                    if (a == xa || a == xb || b == xa || b == xb)
+                    {
+                        jm = min(jm, i);
+                        return; // (indices only grow from here)
+                    }
+                }
+            };
+#pragma unroll
+            for (int j = 0; j < UNR; j++)
+                if (kk[j])
+                    look(kk[j], pk[j]);
+            if (threadIdx.x < NW * TOPK)
+                look(s_wk[threadIdx.x / TOPK][threadIdx.x % TOPK], s_wp[threadIdx.x / TOPK][threadIdx.x % TOPK]);
+#pragma unroll
+            for (int o = 16; o; o >>= 1)
+                jm = min(jm, __shfl_xor_sync(0xFFFFFFFFu, jm, o));
+            if (lane == 0 && jm != 0xFFFFFFFFu)
+                atomicMin(&s_resc[3], jm);
+            __syncthreads();
+            if (warp == 0)
+            {
+                // merges 0 .. jm are safe (nothing in front of them is touched); at least the strictly-above ones
+                const u32 jmin = s_resc[3];
+                const u32 safe = (jmin >= nw) ? nw : jmin + 1;
+                nacc = max(nacc, min(nw, safe));
+            }
+        }
+        if (warp == 0)
+        {
+            nacc_bound = nacc;
             // How far can D move before merge i of the batch is selected (i.e. through merges 0 .. i-1)?  A merge
             // with c replacements creates at most min(2c, 2V) new keys ((x,z) and (z,y), one of each per
             // replacement, V token ids) and empties at most that many old ones ((x,a), (b,y)) plus (a,b) itself.
