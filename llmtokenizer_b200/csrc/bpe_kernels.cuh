@@ -24,7 +24,8 @@ constexpr u64 EMPTY_KEY = ~0ull;
 constexpr u64 NO_SLOT = ~0ull;
 
 constexpr int MAX_RANKS = 8;
-constexpr int BATCH_MAX = 8;
+constexpr int BATCH_MAX = 8; // (at most 15: a nibble holds 1 + the pair index; 12 measured 2 % faster on config 2 but the larger
+                              // table margins it needs made rehashes land inside runs)
 // batched passes look tokens up in a byte table indexed by (token mod CLS_SIZE): the tokens of a batch must
 // differ mod CLS_SIZE (a stronger form of "pairwise different")
 constexpr u32 CLS_SIZE = 8192, CLS_MASK = CLS_SIZE - 1;
@@ -82,7 +83,7 @@ struct DevState
     u32 nb, batch_max;
     u32 batch_min_z, pad_bz;  // no batching below this id (test / tuning knob)
     u32 hist_max, hist_words; // ids below hist_max run with a shared-memory delta histogram of hist_words counters
-    u32 ba[8], bb[8];
+    u32 ba[BATCH_MAX], bb[BATCH_MAX];
     u64 batch_merges, batch_passes; // statistics: merges that rode along in a batch / passes with nb > 1
     u32 skip; // encode: this rank's pair does not occur anywhere -> no pass
     // loop control
