@@ -877,7 +877,7 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
         }
         else if (!X.ranged && h->layout == LAYOUT_RANGED)
         {
-            repack_kernel<<<RANGE_MAX, 256, 0, c->stream>>>(c->d_st);
+            repack_kernel<<<RANGE_MAX, 1024, 0, c->stream>>>(c->d_st);
             c->launches++;
         }
         if ((rc = enqueue_batch(c, X, encode)))
@@ -937,7 +937,7 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
     }
     if (c->h_st->layout == LAYOUT_RANGED)
     {
-        repack_kernel<<<RANGE_MAX, 256, 0, c->stream>>>(c->d_st);
+        repack_kernel<<<RANGE_MAX, 1024, 0, c->stream>>>(c->d_st);
         c->launches++;
         CU(cudaGetLastError());
         if ((rc = poll_state(c)))
@@ -1270,7 +1270,7 @@ static int resolve_pause(bpe_cuda_ctx *c, bool encode)
     if (h->layout == LAYOUT_RANGED)
     {
         // everything below works on positions of one dense array
-        repack_kernel<<<RANGE_MAX, 256, 0, c->stream>>>(c->d_st);
+        repack_kernel<<<RANGE_MAX, 1024, 0, c->stream>>>(c->d_st);
         c->launches++;
     }
     if (pause & PAUSE_SAME)

@@ -750,12 +750,12 @@ __global__ void __launch_bounds__(RANGE_MAX) partition_kernel(DevState *st)
 // is the sum of the lower ranges' lengths: <= 320 numbers, summed by every CTA for itself).  The last
 // CTA to finish flips the buffers.  Runs whatever the loop state is (the host asks for it on pauses
 // and before the final download).
-__global__ void __launch_bounds__(256) repack_kernel(DevState *st)
+__global__ void __launch_bounds__(1024) repack_kernel(DevState *st)
 {
     if (st->layout != LAYOUT_RANGED)
         return;
     __shared__ u64 s_off;
-    __shared__ u64 s_w[8];
+    __shared__ u64 s_w[32];
     const u32 nr = st->nr, c = blockIdx.x;
     const u32 *cnt = st->rcnt[st->cur];
     if (c < nr)
@@ -772,7 +772,7 @@ __global__ void __launch_bounds__(256) repack_kernel(DevState *st)
         if (threadIdx.x == 0)
         {
             u64 t = 0;
-            for (int w = 0; w < 8; w++)
+            for (u32 w = 0; w < blockDim.x / 32; w++)
                 t += s_w[w];
             s_off = t;
         }
@@ -780,7 +780,18 @@ __global__ void __launch_bounds__(256) repack_kernel(DevState *st)
         const u32 *src = st->tok[st->cur] + (u64)c * st->rcap;
         u32 *dst = (st->tok_real[0] == st->tok[st->cur] ? st->tok_real[1] : st->tok_real[0]) + s_off;
         const u32 m = cnt[c];
-        for (u32 i = threadIdx.x; i < m; i += blockDim.x)
+        // four independent loads per thread and trip: a copy lives on the bytes it keeps in flight
+        const u32 B = blockDim.x;
+        u32 i = threadIdx.x;
+        for (; i + 3 * B < m; i += 4 * B)
+        {
+            const u32 v0 = src[i], v1 = src[i + B], v2 = src[i + 2 * B], v3 = src[i + 3 * B];
+            dst[i] = v0;
+            dst[i + B] = v1;
+            dst[i + 2 * B] = v2;
+            dst[i + 3 * B] = v3;
+        }
+        for (; i < m; i += B)
             dst[i] = src[i];
     }
     __syncthreads();
