@@ -195,8 +195,9 @@ struct bpe_cuda_ctx
     // options
     int profile_replace = 0;
     int batch_steps = 64;
-    int smem_hist_max_vocab = 640;  // ids below this: one merge per pass, deltas privatised in shared memory (10 KB); measured
-                                    // on config 2: 1792 -> 209 ms, 1024 -> 186, 768 -> 181, 512 -> 180, 384 -> 183
+    int smem_hist_max_vocab = 448;  // ids below this: one merge per pass, deltas privatised in shared memory (7 KB); above: batched
+                                    // passes with global RED.  Measured on config 2 (final batching rules): 320 -> 138.8 ms,
+                                    // 448 -> 137.3, 512 -> 139.3, 640 -> 141.8 (with the first rules: 1792 -> 209, 640 -> 182)
     int force_census = 0;
     int use_stream = 1;
     int replace_occ[2] = {0, 0};
