@@ -599,16 +599,31 @@ static int choose_candidates(bpe_cuda_ctx *c, u32 best)
     int rc;
     if (best >= 8)
     {
-        u32 T = best / 2;
+        // Start at half the maximum and move the threshold up until the list fits the registers of the
+        // selecting block (CAND_TARGET leaves room for the pairs that will cross the threshold later); a
+        // threshold closer to the maximum is outlived sooner, so stop at 15/16.  If the counts are too flat
+        // for that, any list that fits the buffer will do (whole-list gathers, no batches).
+        u32 T = best / 2, T_usable = 0;
         for (int tries = 0; tries < 4 && T < best; tries++)
         {
             if ((rc = rebuild_candidates(c, T)))
                 return rc;
             if ((rc = poll_state(c)))
                 return rc;
-            if (!c->h_st->cand_overflow && c->h_st->ncand <= CAND_CAP / 2)
+            const bool usable = !c->h_st->cand_overflow && c->h_st->ncand <= CAND_CAP / 2;
+            if (usable && c->h_st->ncand <= CAND_TARGET)
                 return 0;
+            if (usable && !T_usable)
+                T_usable = T; // the lowest threshold whose list fits the buffer: it lives longest
             T += (best - T + 1) / 2;
+        }
+        if (T_usable)
+        {
+            if ((rc = rebuild_candidates(c, T_usable)))
+                return rc;
+            cand_big_ok_kernel<<<1, 1, 0, c->stream>>>(c->d_st);
+            c->launches++;
+            return poll_state(c);
         }
     }
     c->list_retry_below = best / 2;

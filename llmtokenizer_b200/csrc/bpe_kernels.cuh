@@ -120,6 +120,7 @@ struct DevState
     u32 *cand;
     u32 *cflag;
     u32 ncand, cand_cap, cand_T, cand_overflow;
+    u32 cand_big_ok, pad_cb; // the host found no threshold that keeps the list within CAND_FIT entries: do not ask again
     u32 pending, pad_pend; // a merge is committed and its pass / delta application is still to come
     // scheduling counters
     u32 ticket, sel_done;
@@ -770,6 +771,9 @@ __device__ inline void extend_batch(DevState *st, u32 a, u32 b)
 }
 
 constexpr int SEL_THREADS = 512;
+// candidates the last block of apply_select_kernel keeps in registers (8 per thread); batches are only formed
+// from such a list, so the host aims below it and the device asks for a new threshold when the list outgrows it
+constexpr u32 CAND_FIT = SEL_THREADS * 8, CAND_TARGET = 3072;
 
 // What the batch extension needs to know about the merge decide_list() has just committed (shared memory)
 struct Committed
@@ -787,11 +791,12 @@ struct Committed
 // decide() for the list mode on one GPU (the per-pass critical path): the same decisions, but every
 // field is loaded up front in one burst (the loads overlap; in decide()/commit_merge() each load waits for the
 // stores in front of it, five serial round trips to L2) and the merge is committed from registers.
-__device__ inline void decide_list(DevState *st, u64 k, u64 s, u32 m, const PreDecide *pre, Committed *out)
+__device__ inline void decide_list(DevState *st, u64 k, u64 s, u32 m, const PreDecide *pre, Committed *out, u32 ncand)
 {
     const u64 D = (u64)st->distinct, md = st->merges_done, mm = st->max_merges, n_local = st->n, bt0 = st->bt[0];
     const u32 cand_T = st->cand_T, stat = st->static_mode, wr = st->want_ranged, epoch = st->epoch;
     const u32 batch_max = st->batch_max, batch_min_z = st->batch_min_z, hist_max = st->hist_max, hist_words = st->hist_words;
+    const u32 big_ok = st->cand_big_ok;
     u32 *merges = st->merges;
     u64 *n_hist = st->n_hist;
     const u64 key = (s != NO_SLOT) ? __ldcg(st->tkey + s) : 0ull;
@@ -810,6 +815,14 @@ __device__ inline void decide_list(DevState *st, u64 k, u64 s, u32 m, const PreD
     if (D == 0 || m == 0 || freq <= 1 || md >= mm) // bpe.c:730, bpe.c:745, cap
     {
         st->stop = STOP_DONE;
+        return;
+    }
+    if (cand_T && ncand > CAND_FIT && !big_ok && batch_max > 1 && wr && !stat)
+    {
+        // the list has outgrown the registers of this block (no batches, and a gather per entry): the host
+        // rebuilds it with a higher threshold (k is the true maximum here, so nothing is lost)
+        st->pause = PAUSE_REBUILD;
+        st->stop = STOP_PAUSE;
         return;
     }
     if (!stat && n_local < STATIC_LIMIT)
@@ -1732,7 +1745,7 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
         bool extend = false;
         if (st->world == 1 && s_pre.valid)
         {
-            decide_list(st, k, s, m, &s_pre, &s_cm);
+            decide_list(st, k, s, m, &s_pre, &s_cm, ncr);
             extend = fits && s_cm.ok;
         }
         else
@@ -2049,6 +2062,7 @@ __global__ void cand_reset_kernel(DevState *st)
 {
     st->ncand = 0;
     st->cand_overflow = 0;
+    st->cand_big_ok = 0;
     st->cand_T = 0;
 }
 
@@ -2070,6 +2084,8 @@ __global__ void __launch_bounds__(256) cand_rebuild_kernel(DevState *st, u32 T)
     if (blockIdx.x == 0 && threadIdx.x == 0)
         st->cand_T = T;
 }
+
+__global__ void cand_big_ok_kernel(DevState *st) { st->cand_big_ok = 1; }
 
 // halos of the untouched stream (before the first merge), for the shard-straddling byte pair
 __global__ void resolve_edges_kernel(DevState *st, const int32_t *delta_reduced)
