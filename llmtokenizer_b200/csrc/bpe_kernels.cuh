@@ -24,12 +24,14 @@ constexpr u64 EMPTY_KEY = ~0ull;
 constexpr u64 NO_SLOT = ~0ull;
 
 constexpr int MAX_RANKS = 8;
-constexpr int BATCH_MAX = 8; // (at most 15: a nibble holds 1 + the pair index; 12 measured 2 % faster on config 2 but the larger
-                              // table margins it needs made rehashes land inside runs)
+#ifndef BPE_BATCH_MAX
+#define BPE_BATCH_MAX 8
+#endif
+constexpr int BATCH_MAX = BPE_BATCH_MAX; // merges per pass (at most 15: a nibble holds 1 + the pair index)
 // batched passes look tokens up in a byte table indexed by (token mod CLS_SIZE): the tokens of a batch must
 // differ mod CLS_SIZE (a stronger form of "pairwise different")
 constexpr u32 CLS_SIZE = 8192, CLS_MASK = CLS_SIZE - 1;
-__host__ __device__ inline bool tok_alias(u32 x, u32 y) { return ((x ^ y) & CLS_MASK) == 0; } // merges per pass
+__host__ __device__ inline bool tok_alias(u32 x, u32 y) { return ((x ^ y) & CLS_MASK) == 0; }
 constexpr int REC_INTS = 8;                    // one edge record
 constexpr int HDR_INTS = MAX_RANKS * REC_INTS; // edge records sit in front of the delta vectors
 
