@@ -31,9 +31,9 @@ def _stale(target, sources):
 
 def build_engine(force=False):
     src = os.path.join(PKG, "csrc", "bpe_engine.cu")
-    deps = [src, os.path.join(PKG, "csrc", "bpe_kernels.cuh"), os.path.join(PKG, "csrc", "bpe_resolver.cuh"),
-            os.path.join(ROOT, "include", "bpe_cuda.h")]
-    deps = [d for d in deps if os.path.exists(d)]
+    csrc = os.path.join(PKG, "csrc")
+    deps = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh"))]
+    deps.append(os.path.join(ROOT, "include", "bpe_cuda.h"))
     out = os.path.join(PKG, "libbpe_cuda.so")
     if force or _stale(out, deps):
         _run([NVCC, "-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC", "-shared", "-o", out, src, "-ldl"])

@@ -32,6 +32,7 @@
 //                       tokens) goes registers -> global with 128-bit stores realigned by warp
 //                       shuffles; the others compact through a 136-word per-warp staging buffer.
 #pragma once
+#include <type_traits>
 #include "bpe_kernels.cuh"
 
 namespace bpe
@@ -122,13 +123,15 @@ __device__ __forceinline__ void st_v2(u32 *p, u32 x, u32 y) { *reinterpret_cast<
 
 
 // per-stage bookkeeping in shared memory
-struct StageMeta
+template <bool WIDE> struct StageMetaT
 {
     u32 excl;            // output offset of the tile inside the range (running sum)
     u32 slowmask;        // bit j: iteration j has replacements / removals / invalid tokens
     u32 cnt[V_ITERS];    // kept tokens per iteration
     u32 pre[V_ITERS];    // exclusive prefix of cnt
-    unsigned char bits[V_ITERS][32]; // single-merge passes: what iter_bits found, per lane (scanner -> storer)
+    // what the scanner found, per lane, handed to the storers: iter_bits' five bits (one merge per pass), or
+    // those bits << 16 | the four pair nibbles of iter_bits_multi (batched passes, WIDE)
+    typename std::conditional<WIDE, u32, unsigned char>::type bits[V_ITERS][32];
 };
 
 // Replacements that start on my chunk and whether my first token is removed, for iteration j of the
@@ -178,6 +181,15 @@ __device__ __forceinline__ u32 pair_of(u32 x, u32 y, u32 nb, const u32 *ba, cons
         if (x == ba[i] && y == bb[i])
             r = i + 1;
     return r;
+}
+// pair_of through the class table (see iter_bits_multi)
+__device__ __forceinline__ u32 pair_of_cls(u32 x, u32 y, const unsigned char *cls, bool verify, const u32 *ra)
+{
+    const u32 kx = cls[x & CLS_MASK], ky = cls[y & CLS_MASK];
+    u32 m = ((kx & 15u) == (ky >> 4)) ? (kx & 15u) : 0u;
+    if (verify && m && (x != ra[2 * (m - 1)] || y != ra[2 * (m - 1) + 1]))
+        m = 0;
+    return m;
 }
 // as iter_bits; mi = four nibbles, 1 + index of the pair whose replacement starts on token k.  Which pair a
 // token belongs to comes from a byte table in shared memory indexed by (token mod CLS_SIZE): low nibble = 1 +
@@ -284,6 +296,7 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
     unsigned char *s_cls = reinterpret_cast<unsigned char *>(s_hist); // <false> only: token -> pair table of a batched pass
     const bool cls_verify = (z + nb > CLS_SIZE);
     __shared__ __align__(8) u64 s_full[NST], s_scanned[NST], s_ready[NST], s_empty[NST], s_halo_ready;
+    using StageMeta = StageMetaT<!SMEM_HIST>;
     __shared__ StageMeta s_meta[NST];
     __shared__ u32 s_halo[5]; // tokens at range positions -2, -1, n, n+1, n+2
     __shared__ u32 s_ba[BATCH_MAX], s_bb[BATCH_MAX];
@@ -475,6 +488,8 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
                     // ---- pair-count deltas of the replacements that start on my tokens
                     if (nb == 1)
                         sm.bits[j][lane] = (unsigned char)bits;
+                    else if (!SMEM_HIST)
+                        sm.bits[j][lane] = (bits << 16) | mi;
                     if (bits & 0xFu)
                     {
                         const int p0 = j * 128 + lane * 4;
@@ -520,8 +535,8 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
                                 {
                                     // batched: the same ownership rule, with "a replacement" meaning one of any pair
                                     const u32 i = ((mi >> (4 * k)) & 15u) - 1u;
-                                    const u32 pm = pair_of(sin[p - 2], xl, nb, s_ba, s_bb);
-                                    const bool nm = pair_of(yr, sin[p + 3], nb, s_ba, s_bb) != 0;
+                                    const u32 pm = pair_of_cls(sin[p - 2], xl, s_cls, cls_verify, s_ab);
+                                    const bool nm = pair_of_cls(yr, sin[p + 3], s_cls, cls_verify, s_ab) != 0;
                                     const u64 off = (u64)i * 4 * VS;
                                     if (xl != SENT)
                                     {
@@ -651,7 +666,13 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
                         v = full ? 4u : ((p >= valid) ? 0u : ((valid - p < 4u) ? (valid - p) : 4u));
                     }
                     else
-                        iter_bits_multi(sin, j, lane, s_cls, cls_verify, s_ab, valid, full, c, bits, v, mi);
+                    {
+                        const u32 w = sm.bits[j][lane];
+                        bits = w >> 16;
+                        mi = w & 0xFFFFu;
+                        const u32 p = (u32)j * 128u + (u32)lane * 4u;
+                        v = full ? 4u : ((p >= valid) ? 0u : ((valid - p < 4u) ? (valid - p) : 4u));
+                    }
                     const u32 keep = keep_mask(bits, v);
                     const u32 kc = (u32)__popc(keep);
                     // exclusive prefix of the kept counts (0..4 each) from three ballots
