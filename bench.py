@@ -299,6 +299,26 @@ def bench_engine(args, w, rank, world, local):
         encode = {"value": shard.size / (se["ms_device"] * 1e-3) / 1e9, "unit": "GB/s of input", "ranks": int(len(merges_np)),
                   "ms": se["ms_device"], "passes": se["replace_passes"]}
 
+    # ---- full-size self-checks (N = 1, outside every timed region): size-independent properties ----
+    checks = None
+    if world == 1:
+        import hashlib
+        ctx.train(M)
+        m_b, t_b = ctx.download()
+        nbytes = ctx.decode(m_b, download=False)       # ids -> bytes on the device, compared with the shard there
+        mism = ctx.decode_mismatches() if nbytes == shard.size else -1
+        ctx.encode(m_b)
+        _, t_e = ctx.download(merges=False)
+        ctx.set_option("batch_max", 1)                 # one merge per pass: the sequential order by construction
+        ctx.train(M)
+        m_1, t_1 = ctx.download()
+        ctx.set_option("batch_max", 8)
+        sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+        checks = {"decode_round_trip_mismatching_bytes": int(mism),
+                  "batched_passes_equal_one_merge_per_pass": bool(sha(m_b) == sha(m_1) and sha(t_b) == sha(t_1)),
+                  "encode_with_learned_merges_reproduces_training_ids": bool(sha(t_e) == sha(t_b)),
+                  "merges_sha256": sha(m_b)[:16], "ids_sha256": sha(t_b)[:16]}
+
     # ---- CPU reference beside it (rank 0, N = 1 only) ---------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -327,6 +347,7 @@ def bench_engine(args, w, rank, world, local):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "encode": encode,
+            "checks": checks,
             "engine_stats": {k: sp[k] for k in ("same_bucket_ties", "threshold_edges", "resolver_runs", "census_runs",
                                                  "table_rehashes", "table_capacity", "final_distinct", "replace_passes",
                                                  "batch_merges", "batch_passes")},
