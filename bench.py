@@ -318,6 +318,10 @@ def bench_engine(args, w, rank, world, local):
                   "batched_passes_equal_one_merge_per_pass": bool(sha(m_b) == sha(m_1) and sha(t_b) == sha(t_1)),
                   "encode_with_learned_merges_reproduces_training_ids": bool(sha(t_e) == sha(t_b)),
                   "merges_sha256": sha(m_b)[:16], "ids_sha256": sha(t_b)[:16]}
+        gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "c2_full.json")
+        if args.workload == "c2" and os.path.exists(gold):
+            g = json.load(open(gold))       # digests of the CPU oracle's result for this very corpus (tools/make_c2_golden.py)
+            checks["equals_oracle_digest"] = bool(sha(m_b) == g["merges_sha256"] and sha(t_b) == g["ids_sha256"])
 
     # ---- CPU reference beside it (rank 0, N = 1 only) ---------------------------------------------
     cpu = None

@@ -241,6 +241,20 @@ def test_sharded_training_and_encoding_match_oracle(engine, oracle, P):
     assert np.array_equal(ids2, oracle.encode(other, m))
 
 
+def test_config2_full_size_matches_the_oracle_digest(engine):
+    """BASELINE config 2 at its full size (100 MB, 4,096 merges): the oracle needs four minutes for it, so its
+    result is committed as two SHA-256 digests (tests/golden/c2_full.json, tools/make_c2_golden.py)."""
+    import hashlib
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "c2_full.json")))
+    data = corpus(0, g["corpus"]["bytes"], g["corpus"]["seed"])
+    m, t, st = engine.train(data, max_merges=g["merges"])
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a, dtype="<u4").tobytes()).hexdigest()
+    assert len(t) == g["n_ids"] and sha(m) == g["merges_sha256"] and sha(t) == g["ids_sha256"], st
+    assert st["batch_merges"] > 0
+
+
 # ---- decode (SURVEY.md §8f rank 2): ids -> bytes, the inverse of the path ------------------------
 @pytest.mark.parametrize("kind,size,cap", [(0, 300_000, 600), (1, 200_000, 300), (2, 150_000, 200)])
 def test_decode_matches_oracle_and_round_trips(engine, oracle, kind, size, cap):

@@ -1,0 +1,46 @@
+#!/usr/bin/env python3
+"""Full-size parity fixture for config 2: run the CPU oracle (oracle/, pinned against the compiled reference)
+on the exact corpus bench.py uses (zipf_ascii, 100 MB, seed 1234, 4,096 merges; ~4 minutes on one core) and
+record the SHA-256 of the merge list and of the ids.  tests/test_gpu_parity.py and bench.py compare the
+engine's result with these digests.
+
+  python tools/make_c2_golden.py            # writes tests/golden/c2_full.json
+"""
+import hashlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import oracle_api  # noqa: E402
+from llmtokenizer_b200 import _lib  # noqa: E402
+
+SIZE, SEED, VOCAB, MERGES = 100_000_000, 1234, 50000, 4096
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a, dtype="<u4").tobytes()).hexdigest()
+
+
+def main():
+    buf = np.zeros(SIZE, dtype=np.uint8)
+    assert _lib.load_corpus().gen_corpus_fill(0, buf.ctypes.data, SIZE, SEED, VOCAB) == 0
+    t0 = time.time()
+    rc, merges, ids, _ = oracle_api.load().train(buf, MERGES, oracle_api.FAST_CF)
+    assert rc == 0 and len(merges) == MERGES
+    out = {"corpus": {"kind": "zipf_ascii", "bytes": SIZE, "seed": SEED, "words": VOCAB}, "merges": MERGES,
+           "n_ids": int(len(ids)), "merges_sha256": sha(merges), "ids_sha256": sha(ids),
+           "made_by": "tools/make_c2_golden.py (oracle FAST_CF mode)", "oracle_seconds": round(time.time() - t0, 1)}
+    with open(os.path.join(ROOT, "tests", "golden", "c2_full.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print(out)
+
+
+if __name__ == "__main__":
+    main()
