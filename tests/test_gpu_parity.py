@@ -139,7 +139,7 @@ def test_batched_passes_beyond_the_class_table(engine, oracle):
     """Batched passes find a token's pair through an 8,192-entry table indexed by (id mod 8192): once ids
     pass 8,192 they alias table entries, candidates are checked against the real pair, and pairs whose tokens
     alias each other may not share a pass.  10,000 merges on a stream that stays above 1,048,576 tokens;
-    the unbatched engine (itself pinned to the oracle by the tests above) is the checker, the oracle checks
+    checked against the unbatched engine and against the oracle's committed digests; the oracle also checks
     the encoder on a smaller text and the decoder closes the loop."""
     data = corpus(0, 12_000_000, 11)
     cap = 10_000
@@ -157,6 +157,14 @@ def test_batched_passes_beyond_the_class_table(engine, oracle):
     (m, t, st), (m1, t1, s1) = res
     assert len(m) == cap and s1["batch_merges"] == 0
     assert np.array_equal(m, m1) and np.array_equal(t, t1), st
+    # and the oracle itself (three minutes of CPU: committed as digests, tools/make_c2_golden.py zipf12m_10k ...)
+    import hashlib
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "zipf12m_10k.json")))
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a, dtype="<u4").tobytes()).hexdigest()
+    assert (g["corpus"]["bytes"], g["corpus"]["seed"], g["merges"]) == (data.size, 11, cap)
+    assert len(t) == g["n_ids"] and sha(m) == g["merges_sha256"] and sha(t) == g["ids_sha256"]
     ids, se = engine.encode(data, m)
     assert np.array_equal(ids, t) and se["batch_merges"] > 0, se
     other = corpus(0, 400_000, 12)

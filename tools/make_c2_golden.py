@@ -4,7 +4,8 @@ on the exact corpus bench.py uses (zipf_ascii, 100 MB, seed 1234, 4,096 merges; 
 record the SHA-256 of the merge list and of the ids.  tests/test_gpu_parity.py and bench.py compare the
 engine's result with these digests.
 
-  python tools/make_c2_golden.py            # writes tests/golden/c2_full.json
+  python tools/make_c2_golden.py                                   # writes tests/golden/c2_full.json
+  python tools/make_c2_golden.py zipf12m_10k 12000000 11 10000     # name, bytes, seed, merges: other digests
 """
 import hashlib
 import json
@@ -29,6 +30,10 @@ def sha(a):
 
 
 def main():
+    global SIZE, SEED, MERGES
+    name = "c2_full"
+    if len(sys.argv) == 5:
+        name, SIZE, SEED, MERGES = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
     buf = np.zeros(SIZE, dtype=np.uint8)
     assert _lib.load_corpus().gen_corpus_fill(0, buf.ctypes.data, SIZE, SEED, VOCAB) == 0
     t0 = time.time()
@@ -37,7 +42,7 @@ def main():
     out = {"corpus": {"kind": "zipf_ascii", "bytes": SIZE, "seed": SEED, "words": VOCAB}, "merges": MERGES,
            "n_ids": int(len(ids)), "merges_sha256": sha(merges), "ids_sha256": sha(ids),
            "made_by": "tools/make_c2_golden.py (oracle FAST_CF mode)", "oracle_seconds": round(time.time() - t0, 1)}
-    with open(os.path.join(ROOT, "tests", "golden", "c2_full.json"), "w") as f:
+    with open(os.path.join(ROOT, "tests", "golden", name + ".json"), "w") as f:
         json.dump(out, f, indent=1)
     print(out)
 
