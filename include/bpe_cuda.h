@@ -127,7 +127,9 @@ const uint32_t *bpe_cuda_ctx_device_tokens(bpe_cuda_ctx_t *ctx);
 /* Decode this rank's token stream of the last run without leaving the device; the bytes stay in HBM
  * (bpe_cuda_ctx_device_decoded) until the next decode.  _compare counts the bytes that differ from
  * the resident shard (UINT64_MAX when the lengths differ): the round trip decode(encode(x)) == x at
- * full scale with no host copy.  Shards decode independently: no collective. */
+ * full scale with no host copy.  Shards decode independently: no collective.  (With several ranks a merged
+ * token may straddle a shard boundary - it belongs to the left shard - so only the CONCATENATION of the ranks'
+ * decodes equals the corpus; _compare is meant for a single rank.) */
 int bpe_cuda_ctx_decode(bpe_cuda_ctx_t *ctx, const bpe_pair_t *merges, size_t n_merges, size_t *n_bytes);
 int bpe_cuda_ctx_decode_download(bpe_cuda_ctx_t *ctx, uint8_t *bytes);
 int bpe_cuda_ctx_decode_compare(bpe_cuda_ctx_t *ctx, uint64_t *n_diff);
