@@ -263,6 +263,28 @@ def test_config2_full_size_matches_the_oracle_digest(engine):
     assert st["batch_merges"] > 0
 
 
+def test_config3_first_4000_merges_match_the_oracle_digest(engine):
+    """BASELINE config 3's corpus at full size (1 GB of Zipf bytes, 296 full-size ranges, 32-bit counts in the
+    hundreds of millions, several table rehashes, batched passes): its first 4,000 merges cost the oracle an hour,
+    so they are committed as digests (tests/golden/c3_first4000.json, tools/make_c2_golden.py)."""
+    import hashlib
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "c3_first4000.json")))
+    data = corpus(1, g["corpus"]["bytes"], g["corpus"]["seed"])
+    ctx = engine.Context(0)
+    try:
+        ctx.upload(data)
+        st = ctx.train(g["merges"])
+        m, t = ctx.download()
+        assert ctx.decode(m, download=False) == data.size and ctx.decode_mismatches() == 0
+    finally:
+        ctx.close()
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a, dtype="<u4").tobytes()).hexdigest()
+    assert len(t) == g["n_ids"] and sha(m) == g["merges_sha256"] and sha(t) == g["ids_sha256"], st
+    assert st["batch_merges"] > 0
+
+
 # ---- decode (SURVEY.md §8f rank 2): ids -> bytes, the inverse of the path ------------------------
 @pytest.mark.parametrize("kind,size,cap", [(0, 300_000, 600), (1, 200_000, 300), (2, 150_000, 200)])
 def test_decode_matches_oracle_and_round_trips(engine, oracle, kind, size, cap):
