@@ -603,19 +603,40 @@ static int choose_candidates(bpe_cuda_ctx *c, u32 best)
         // selecting block (CAND_TARGET leaves room for the pairs that will cross the threshold later); a
         // threshold closer to the maximum is outlived sooner, so stop at 15/16.  If the counts are too flat
         // for that, any list that fits the buffer will do (whole-list gathers, no batches).
-        u32 T = best / 2, T_usable = 0;
-        for (int tries = 0; tries < 4 && T < best; tries++)
+        u32 T = best / 2, T_usable = 0, T_small = 0;
+        int downs = 0;
+        for (int tries = 0; tries < 4 && T < best && T >= 4;)
         {
             if ((rc = rebuild_candidates(c, T)))
                 return rc;
             if ((rc = poll_state(c)))
                 return rc;
             const bool usable = !c->h_st->cand_overflow && c->h_st->ncand <= CAND_CAP / 2;
+            if (getenv("BPE_CUDA_DEBUG"))
+                fprintf(stderr, "[bpe_cuda] candidate list: best %u threshold %u -> %u entries%s\n", best, T, c->h_st->ncand,
+                        c->h_st->cand_overflow ? " (overflow)" : "");
             if (usable && c->h_st->ncand <= CAND_TARGET)
-                return 0;
+            {
+                // a list of a handful of pairs (steep counts: the first merges of a byte-level corpus) is used up
+                // after a few merges and costs a pause each time: look further down while the list stays small
+                if (c->h_st->ncand >= 128 || downs >= 3 || tries > 0 || T < 64)
+                    return 0;
+                T_small = T;
+                T /= 4;
+                downs++;
+                continue;
+            }
+            if (T_small)
+            {
+                // one step too far down: the previous (short) list it is
+                if ((rc = rebuild_candidates(c, T_small)))
+                    return rc;
+                return poll_state(c);
+            }
             if (usable && !T_usable)
                 T_usable = T; // the lowest threshold whose list fits the buffer: it lives longest
             T += (best - T + 1) / 2;
+            tries++;
         }
         if (T_usable)
         {
@@ -1277,7 +1298,15 @@ static int resolve_pause(bpe_cuda_ctx *c, bool encode)
     if (pause & PAUSE_REBUILD)
     {
         // nothing was committed: new list (or whole-table mode), then select again
-        if ((rc = choose_candidates(c, best)))
+        if (best == 0 && c->cand_T)
+        {
+            // the list ran EMPTY (every listed pair was merged or decayed): nothing says what the maximum is now.
+            // One batch of whole-table selections; the next poll builds a list from the real maximum.
+            if ((rc = rebuild_candidates(c, 0)))
+                return rc;
+            c->list_retry_below = ~0u;
+        }
+        else if ((rc = choose_candidates(c, best)))
             return rc;
         resume_kernel<<<1, 1, 0, c->stream>>>(c->d_st);
         c->launches++;
