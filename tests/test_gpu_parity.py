@@ -263,20 +263,6 @@ def test_config2_full_size_matches_the_oracle_digest(engine):
     assert st["batch_merges"] > 0
 
 
-def test_zipf_bytes_200mb_10000_merges_match_the_oracle_digest(engine):
-    """Byte-level Zipf corpus, 200 MB, 10,000 merges: batched passes with ids beyond the 8,192-entry class table
-    on a stream of 80+ M tokens and a table of millions of pairs (33 minutes of oracle time, committed as digests)."""
-    import hashlib
-    import json
-    import os
-    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "zipfb200m_10k.json")))
-    data = corpus(1, g["corpus"]["bytes"], g["corpus"]["seed"])
-    m, t, st = engine.train(data, max_merges=g["merges"])
-    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a, dtype="<u4").tobytes()).hexdigest()
-    assert len(t) == g["n_ids"] and sha(m) == g["merges_sha256"] and sha(t) == g["ids_sha256"], st
-    assert st["batch_merges"] > 0
-
-
 def test_config3_first_4000_merges_match_the_oracle_digest(engine):
     """BASELINE config 3's corpus at full size (1 GB of Zipf bytes, 296 full-size ranges, 32-bit counts in the
     hundreds of millions, several table rehashes, batched passes): its first 4,000 merges cost the oracle an hour,
@@ -360,3 +346,17 @@ def test_decode_on_device_round_trip(engine):
         assert ctx.decode_mismatches() > 0
     finally:
         ctx.close()
+
+
+def test_zipf_bytes_200mb_10000_merges_match_the_oracle_digest(engine):
+    """Byte-level Zipf corpus, 200 MB, 10,000 merges: batched passes with ids beyond the 8,192-entry class table
+    on a stream of 80+ M tokens and a table of millions of pairs (33 minutes of oracle time, committed as digests)."""
+    import hashlib
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "zipfb200m_10k.json")))
+    data = corpus(1, g["corpus"]["bytes"], g["corpus"]["seed"])
+    m, t, st = engine.train(data, max_merges=g["merges"])
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a, dtype="<u4").tobytes()).hexdigest()
+    assert len(t) == g["n_ids"] and sha(m) == g["merges_sha256"] and sha(t) == g["ids_sha256"], st
+    assert st["batch_merges"] > 0
