@@ -118,3 +118,127 @@ def test_sharded_tiled_rewrite_matches_reference_loop(oracle):
         got[a | (b << 32)] = 0
         got = {k: v for k, v in got.items() if v}
         assert got == after, (it, toks.tolist(), a, b, z, shards, tile)
+
+
+def test_premises_of_the_batched_pass_rules(oracle):
+    """The GPU engine lets a pass carry several merges when they are provably the next ones (batched
+    passes).  The proof rests on three facts about ONE merge (a, b) -> z with c replacements, checked here on the
+    oracle's own merge sequence (CPU only, no engine involved):
+      1. only pairs that contain a, b or z change their count, and those that contain a or b never grow;
+      2. a new pair never exceeds the old pair it comes from: (x, z) <= (x, a), (z, y) <= (b, y), (z, z) <= (b, a);
+      3. the number of distinct pairs D grows by at most min(2c, 2V) and shrinks by at most min(2c, 2V) + 1
+         (V = token ids that exist after the merge)."""
+    rng = np.random.default_rng(11)
+    texts = [rng.integers(97, 103, 30_000, dtype=np.uint8),                                   # few symbols, long merge chains
+             np.repeat(rng.integers(97, 100, 9_000, dtype=np.uint8), rng.integers(1, 5, 9_000)),  # runs: a == b merges
+             np.frombuffer((b"the quick brown fox jumps over the lazy dog " * 700), dtype=np.uint8)]
+    for text in texts:
+        rc, merges, ids, _ = oracle.train(text, 120, FAST)
+        assert rc == 0
+        toks = text.astype(np.uint32)
+        before = oracle_api.pair_counts(toks)
+        for r, (a, b) in enumerate(merges.tolist()):
+            z = 256 + r
+            c_ab = before.get(a | (b << 32), 0)
+            nxt = oracle.rewrite(toks, a, b, z)
+            after = oracle_api.pair_counts(nxt)
+            c = (len(toks) - len(nxt))                     # replacements made (a == b: pairs of a run, <= c_ab)
+            assert c <= c_ab and (a == b or c == c_ab)
+            V = z + 1
+            for key in set(before) | set(after):
+                x, y = key & 0xFFFFFFFF, key >> 32
+                old, new = before.get(key, 0), after.get(key, 0)
+                if old != new:
+                    assert {x, y} & {a, b, z}, (r, x, y)                               # 1: nothing else moves
+                if z not in (x, y):
+                    assert new <= old, (r, x, y, old, new)                             # 1: old pairs never grow
+                elif x == z and y == z:
+                    assert new <= before.get(b | (a << 32), 0)                         # 2
+                elif y == z:
+                    assert new <= before.get(x | (a << 32), 0), (r, x, new)            # 2
+                else:
+                    assert new <= before.get(b | (y << 32), 0), (r, y, new)            # 2
+            bound = min(2 * c, 2 * V)
+            assert len(after) - len(before) <= bound and len(before) - len(after) <= bound + 1, (r, len(before), len(after), c)
+            toks, before = nxt, after
+        assert np.array_equal(toks, ids)
+
+
+@pytest.mark.parametrize("kind", ["zipf_words", "near_uniform"])
+def test_batch_walk_rules_predict_the_oracles_next_merges(oracle, kind):
+    """The rules by which apply_select_kernel lets a pass carry several merges (disjoint tokens, no
+    same-bucket tie, strictly above the bound - or equal to it and untouched -, D clear of every doubling threshold),
+    restated here in Python and run against the oracle's own merge order: every batch they form must be exactly the
+    oracle's next merges, in order.  (The CUDA implementation of the same rules is checked by the -m gpu tests.)"""
+    from llmtokenizer_b200 import _lib
+    if kind == "zipf_words":
+        text = np.zeros(400_000, dtype=np.uint8)
+        assert _lib.load_corpus().gen_corpus_fill(0, text.ctypes.data, text.size, 5, 50000) == 0
+        cap = 500
+    else:   # 40 almost equally frequent symbols: late counts tie all the time, the equal-count rule decides
+        text = np.random.default_rng(3).integers(40, 80, 300_000, dtype=np.uint8)
+        cap = 700
+    rc, merges, ids, _ = oracle.train(text, cap, FAST_CF)
+    assert rc == 0 and len(merges) == cap
+    merges = [tuple(m) for m in merges.tolist()]
+    mm3, buckets = oracle.lib.bo_murmur3_pair, oracle.lib.bo_merged_buckets
+    toks = text.astype(np.uint32)
+    r, batches, carried = 0, 0, 0
+    while r < cap:
+        counts = oracle_api.pair_counts(toks)
+        D = len(counts)
+        B = buckets(D)
+        order = sorted(((cnt, mm3(k & 0xFFFFFFFF, k >> 32) % B, k) for k, cnt in counts.items() if cnt >= 2),
+                       key=lambda e: (-e[0], e[1]))[:200]
+        assert (order[0][2] & 0xFFFFFFFF, order[0][2] >> 32) == merges[r] or order[0][:2] == order[1][:2]
+        acc = [merges[r]]                           # what decide() committed; the walk extends it
+        acc_cnt = [counts[merges[r][0] | (merges[r][1] << 32)]]
+        bound, rescue_ok = 0, True
+        if merges[r][0] != merges[r][1] and order[0][:2] != order[1][:2]:
+            for i in range(1, len(order)):
+                cnt, bkt, k = order[i]
+                a, b = k & 0xFFFFFFFF, k >> 32
+                tie = (i + 1 < len(order) and order[i + 1][:2] == (cnt, bkt)) or order[i - 1][:2] == (cnt, bkt)
+                overlap = any(t in (a, b) for p in acc for t in p)
+                if tie or a == b or overlap or len(acc) >= 8:
+                    bound, rescue_ok = cnt, not tie
+                    break
+                acc.append((a, b))
+                acc_cnt.append(cnt)
+            else:
+                bound = order[-1][0]                # (the walk never gets this far: 200 candidates, 8 merges)
+            n = sum(1 for c in acc_cnt if c > bound)
+            if rescue_ok and n < len(acc):
+                # merges whose count equals the bound survive unless a pair of exactly that count touches a merge in front
+                jmin = len(acc)
+                for cnt, _, k in order:
+                    a, b = k & 0xFFFFFFFF, k >> 32
+                    if cnt == bound and (a, b) not in acc:
+                        for j, p in enumerate(acc):
+                            if a in p or b in p:
+                                jmin = min(jmin, j)
+                                break
+                n = max(n, min(len(acc), jmin + 1))
+            n = max(n, 1)
+            # D may move by min(2c, 2V) (+1 downwards) per merge in front: B(D) must not be able to change
+            V, up, down = 256 + r + 8, 0, 0
+            for j in range(1, n):
+                up += min(2 * acc_cnt[j - 1], 2 * V)
+                down += min(2 * acc_cnt[j - 1], 2 * V) + 1
+                if buckets(max(D - down - 1, 0)) != buckets(D + up + 1):
+                    n = j
+                    break
+            acc = acc[:n]
+        else:
+            acc = acc[:1]
+        acc = acc[:cap - r]                         # (the engine's `room`: the merge cap ends a batch)
+        assert acc == merges[r:r + len(acc)], (r, acc, merges[r:r + len(acc)])
+        batches += 1
+        carried += len(acc) - 1
+        for a, b in acc:
+            toks = oracle.rewrite(toks, a, b, 256 + r)
+            r += 1
+            if r >= cap:
+                break
+    assert np.array_equal(toks, ids)
+    assert carried > cap // 8, (batches, carried)       # the rules are not vacuous: many merges ride along
