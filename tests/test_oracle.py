@@ -164,16 +164,18 @@ def test_premises_of_the_batched_pass_rules(oracle):
         assert np.array_equal(toks, ids)
 
 
-@pytest.mark.parametrize("kind", ["zipf_words", "near_uniform"])
+@pytest.mark.parametrize("kind", ["zipf_words", "zipf_bytes", "near_uniform"])
 def test_batch_walk_rules_predict_the_oracles_next_merges(oracle, kind):
     """The rules by which apply_select_kernel lets a pass carry several merges (disjoint tokens, no
     same-bucket tie, strictly above the bound - or equal to it and untouched -, D clear of every doubling threshold),
     restated here in Python and run against the oracle's own merge order: every batch they form must be exactly the
     oracle's next merges, in order.  (The CUDA implementation of the same rules is checked by the -m gpu tests.)"""
     from llmtokenizer_b200 import _lib
-    if kind == "zipf_words":
+    if kind in ("zipf_words", "zipf_bytes"):
         text = np.zeros(400_000, dtype=np.uint8)
-        assert _lib.load_corpus().gen_corpus_fill(0, text.ctypes.data, text.size, 5, 50000) == 0
+        assert _lib.load_corpus().gen_corpus_fill(0 if kind == "zipf_words" else 1, text.ctypes.data, text.size, 5,
+                                                  50000 if kind == "zipf_words" else 65536) == 0
+        text = text[:len(text.tobytes().split(b"\0")[0])]
         cap = 500
     else:   # 40 almost equally frequent symbols: late counts tie all the time, the equal-count rule decides
         text = np.random.default_rng(3).integers(40, 80, 300_000, dtype=np.uint8)
