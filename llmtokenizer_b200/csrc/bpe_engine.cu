@@ -165,6 +165,9 @@ struct bpe_cuda_ctx
     int ranges_opt = 0;      // test knob: number of ranges (0 = two per SM)
     int want_ranged = 0;     // this run uses the streaming kernel (RANGED layout) for its a != b passes
     u32 list_retry_below = ~0u; // whole-table mode: try a list again once the best count is below this
+    bool fresh_select = false;  // the candidate list ran empty: one whole-table selection must say what the maximum is now
+                                // before any new list is chosen (the control block's `freq` is stale until then)
+    bool debug = false;         // BPE_CUDA_DEBUG (read once per context)
     // logs
     u32 *d_merges = nullptr;
     u64 *d_nhist = nullptr;
@@ -432,7 +435,7 @@ static int table_rehash(bpe_cuda_ctx *c, u64 new_cap)
 
 static int check_state(bpe_cuda_ctx *c)
 {
-    if (getenv("BPE_CUDA_DEBUG"))
+    if (c->debug)
         fprintf(stderr, "[bpe_cuda r%d] merges=%llu n=%llu n_global=%llu D=%lld occ=%llu cap=%llu stop=%u pause=%u static=%u err=%u a=%u b=%u f=%u mult=%u\n",
                 c->rank, c->h_st->merges_done, c->h_st->n, c->h_st->n_global, c->h_st->distinct, c->h_st->occupied, c->h_st->tcap,
                 c->h_st->stop, c->h_st->pause, c->h_st->static_mode, c->h_st->err, c->h_st->a, c->h_st->b, c->h_st->freq,
@@ -612,9 +615,21 @@ static int choose_candidates(bpe_cuda_ctx *c, u32 best)
             if ((rc = poll_state(c)))
                 return rc;
             const bool usable = !c->h_st->cand_overflow && c->h_st->ncand <= CAND_CAP / 2;
-            if (getenv("BPE_CUDA_DEBUG"))
+            if (c->debug)
                 fprintf(stderr, "[bpe_cuda] candidate list: best %u threshold %u -> %u entries%s\n", best, T, c->h_st->ncand,
                         c->h_st->cand_overflow ? " (overflow)" : "");
+            if (c->h_st->ncand == 0)
+            {
+                // Nothing reaches T: `best` did not describe the table (the maximum has dropped by more than half
+                // since it was read).  An empty list can never be accepted - the next selection would find nothing,
+                // ask for a rebuild and land here again: whole-table selection until a real maximum is known.
+                if (T_small)
+                    break;
+                c->list_retry_below = T;
+                if ((rc = rebuild_candidates(c, 0)))
+                    return rc;
+                return poll_state(c);
+            }
             if (usable && c->h_st->ncand <= CAND_TARGET)
             {
                 // a list of a handful of pairs (steep counts: the first merges of a byte-level corpus) is used up
@@ -627,16 +642,17 @@ static int choose_candidates(bpe_cuda_ctx *c, u32 best)
                 continue;
             }
             if (T_small)
-            {
-                // one step too far down: the previous (short) list it is
-                if ((rc = rebuild_candidates(c, T_small)))
-                    return rc;
-                return poll_state(c);
-            }
+                break; // one step too far down: the previous (short) list it is
             if (usable && !T_usable)
                 T_usable = T; // the lowest threshold whose list fits the buffer: it lives longest
             T += (best - T + 1) / 2;
             tries++;
+        }
+        if (T_small)
+        {
+            if ((rc = rebuild_candidates(c, T_small)))
+                return rc;
+            return poll_state(c);
         }
         if (T_usable)
         {
@@ -813,14 +829,31 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
 {
     int rc;
     c->list_retry_below = ~0u;
+    c->fresh_select = false;
     if ((rc = poll_state(c)))
         return rc;
+    // watchdog: every trip through this loop must commit a merge (or a rank) sooner or later; a run of trips
+    // that leaves merges_done where it was is a host-side logic error and must end as one, not spin
+    u64 wd_merges = ~0ull;
+    int wd_trips = 0;
     for (;;)
     {
         // ---- the queue is drained and c->h_st is current
         DevState *h = c->h_st;
         if (h->stop == STOP_DONE)
             break;
+        if (h->merges_done != wd_merges)
+        {
+            wd_merges = h->merges_done;
+            wd_trips = 0;
+        }
+        else if (++wd_trips > 24)
+        {
+            set_error("no progress after %d host round trips at merge %llu (stop %u pause 0x%x pending %u list threshold %u, "
+                      "%u candidates, best count %u)", wd_trips, (unsigned long long)h->merges_done, h->stop, h->pause, h->pending,
+                      h->cand_T, h->ncand, (u32)(h->sel_key >> 32));
+            return BPE_CUDA_ERR_STATE;
+        }
         if (h->stop == STOP_PAUSE)
         {
             if ((rc = resolve_pause(c, encode)))
@@ -829,20 +862,25 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
                 return rc;
             continue;
         }
-        if (!encode && h->merges_done == 0 && !h->pending)
+        if (!encode && !h->pending && (h->merges_done == 0 || c->fresh_select))
         {
-            // the very first selection (whole table): its count sizes the candidate list
-            if ((rc = ensure_logs(c, 2)))
+            // The very first selection, or the first one after the candidate list ran empty: on the whole table.
+            // Only its count says what the maximum is now, so only it may size the next candidate list (the
+            // control block's `freq` still holds the count of the last COMMITTED merge, bpe.c:737-743).
+            c->fresh_select = false;
+            if ((rc = ensure_logs(c, (size_t)h->merges_done + 2)))
+                return rc;
+            if (c->cand_T && (rc = rebuild_candidates(c, 0)))
                 return rc;
             if ((rc = enqueue_select(c, encode)))
                 return rc;
             CU(cudaGetLastError());
             if ((rc = poll_state(c)))
                 return rc;
-            if (c->h_st->stop == STOP_RUN && c->h_st->pending && (rc = choose_candidates(c, c->h_st->freq)))
+            if (!(c->h_st->stop == STOP_RUN && c->h_st->pending))
+                continue; // stopped or paused instead of committing
+            if ((rc = choose_candidates(c, c->h_st->freq)))
                 return rc;
-            if (c->h_st->merges_done == 0)
-                continue; // stopped or paused before committing anything
             h = c->h_st;
         }
         BatchPlan X;
@@ -878,8 +916,8 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
         if (!encode)
         {
             const u32 T0 = c->cand_T;
-            if (T0 == 0 && h->freq >= 16 && h->freq < c->list_retry_below)
-                rc = choose_candidates(c, h->freq);
+            if (T0 == 0 && h->pending && h->freq >= 16 && h->freq < c->list_retry_below)
+                rc = choose_candidates(c, h->freq); // (pending: `freq` is the count of a merge that is still in the table)
             else if (T0 && (h->cand_overflow || h->ncand > CAND_CAP * 3 / 4))
                 rc = choose_candidates(c, std::max<u32>(h->freq, T0 + 1));
             if (rc)
@@ -1189,16 +1227,16 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
     CU(cudaEventDestroy(ev1));
 
     DevState *h = c->h_st;
-    if (getenv("BPE_CUDA_DEBUG"))
+    if (c->debug)
         fprintf(stderr, "[bpe_cuda] host ms: rehash %.1f | candidates %.1f | pauses %.1f | poll waits %.1f | enqueue %.1f\n", c->host_ms[0],
                 c->host_ms[1], c->host_ms[2], c->host_ms[3], c->host_ms[4]);
-    if (getenv("BPE_CUDA_DEBUG") && h->dbg[6])
+    if (c->debug && h->dbg[6])
         fprintf(stderr, "[bpe_cuda] apply+select phases, avg ns over %llu launches: apply %.0f | done-atomic %.0f | last-block setup %.0f | "
                         "candidate scan %.0f | reduce %.0f | decide %.0f | batch extension %.0f\n",
                 h->dbg[6], (double)h->dbg[0] / h->dbg[6], (double)h->dbg[1] / h->dbg[6], (double)h->dbg[2] / h->dbg[6],
                 (double)h->dbg[3] / h->dbg[6], (double)h->dbg[4] / h->dbg[6], (double)h->dbg[5] / h->dbg[6],
                 (double)h->dbg[7] / h->dbg[6]);
-    if (getenv("BPE_CUDA_DEBUG"))
+    if (c->debug)
         fprintf(stderr, "[bpe_cuda] batch walks ended by: cap %llu | below cand_T %llu | tie %llu | overlap %llu | a==b/alias %llu | list used up %llu | merges trimmed by the bound %llu, by the D margin %llu\n",
                 (unsigned long long)h->ext_why[0], (unsigned long long)h->ext_why[1], (unsigned long long)h->ext_why[2],
                 (unsigned long long)h->ext_why[3], (unsigned long long)h->ext_why[4], (unsigned long long)h->ext_why[5], (unsigned long long)h->ext_why[6], (unsigned long long)h->ext_why[7]);
@@ -1301,10 +1339,11 @@ static int resolve_pause(bpe_cuda_ctx *c, bool encode)
         if (best == 0 && c->cand_T)
         {
             // the list ran EMPTY (every listed pair was merged or decayed): nothing says what the maximum is now.
-            // One batch of whole-table selections; the next poll builds a list from the real maximum.
+            // run_loop makes ONE whole-table selection and builds the next list from the count it finds.
             if ((rc = rebuild_candidates(c, 0)))
                 return rc;
             c->list_retry_below = ~0u;
+            c->fresh_select = true;
         }
         else if ((rc = choose_candidates(c, best)))
             return rc;
@@ -1412,6 +1451,7 @@ int bpe_cuda_ctx_create(int device, bpe_cuda_ctx_t **out)
     }
     bpe_cuda_ctx *c = new bpe_cuda_ctx();
     c->device = device;
+    c->debug = getenv("BPE_CUDA_DEBUG") != nullptr;
     c->sm_count = prop.multiProcessorCount;
     if (const char *e = getenv("BPE_CUDA_INPLACE"))
         c->inplace = atoi(e);
@@ -1426,7 +1466,7 @@ int bpe_cuda_ctx_create(int device, bpe_cuda_ctx_t **out)
             cudaGetLastError();
             c->l2_window_max = 0;
         }
-        if (getenv("BPE_CUDA_DEBUG"))
+        if (c->debug)
             fprintf(stderr, "[bpe_cuda] L2 %d MB, persisting max %zu MB, window max %zu MB\n", prop.l2CacheSize >> 20,
                     c->l2_persist_bytes >> 20, c->l2_window_max >> 20);
     }

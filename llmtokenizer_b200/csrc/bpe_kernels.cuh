@@ -786,6 +786,7 @@ struct Committed
     u64 merges_done;    // after the commit
     u64 max_merges;
     u64 bt0;            // worker-table buckets after the commit
+    u64 n_stream;       // tokens in the (global) stream the committed merge is applied to
     u32 *merges;
     u64 *n_hist;
 };
@@ -887,6 +888,7 @@ __device__ inline void decide_list(DevState *st, u64 k, u64 s, u32 m, const PreD
     out->merges_done = md + 1;
     out->max_merges = mm;
     out->bt0 = bt_new;
+    out->n_stream = n_local;
     out->merges = merges;
     out->n_hist = n_hist;
 }
@@ -1769,6 +1771,7 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
                 s_cm.merges_done = st->merges_done;
                 s_cm.max_merges = st->max_merges;
                 s_cm.bt0 = st->bt[0];
+                s_cm.n_stream = st->n_global;
                 s_cm.merges = st->merges;
                 s_cm.n_hist = st->n_hist;
             }
@@ -2002,9 +2005,24 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
             }
             up = __shfl_up_sync(0xFFFFFFFFu, up, 1); // merges 0 .. lane-1
             down = __shfl_up_sync(0xFFFFFFFFu, down, 1);
+            // tokens the merges in front of this one remove (a != b: one per occurrence)
+            u64 gone = ((u32)lane < nacc) ? (u64)my_c : 0ull;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const u64 g2 = __shfl_up_sync(0xFFFFFFFFu, gone, o);
+                if (lane >= o)
+                    gone += g2;
+            }
+            gone = __shfl_up_sync(0xFFFFFFFFu, gone, 1);
             bool clear = true;
             if (lane >= 1 && (u32)lane < nacc)
             {
+                // The reference switches to its 16 static slices in the first iteration that starts below
+                // 1,048,576 tokens (bpe.c:449), and from then on the worker tables grow with their slices'
+                // contents: that iteration must be selected on its own (census), not ride along in this pass.
+                if (cm.n_stream < STATIC_LIMIT + gone)
+                    clear = false;
                 for (u64 bsz = 65536; bsz <= (1ull << 40); bsz *= 2)
                 {
                     const u64 thr = resize_threshold(bsz);

@@ -1,38 +1,116 @@
 """GPU suite (-m gpu): the CUDA engine, called through its C ABI, against the committed reference
-fixtures and the CPU oracle on the same seeded inputs.  Bit-exact: merge list, ids."""
+fixtures and the CPU oracle on the same seeded inputs.  Bit-exact: merge list, ids.
+
+Small inputs run the oracle inline; the heavier seeded cases compare with the oracle's committed results
+(tests/parity_cases.py, tests/golden/cases/, made offline by tools/make_case_digests.py) so that the whole
+suite stays inside the GPU box's time budget."""
 import numpy as np
 import pytest
 
 import oracle_api
+import parity_cases as pc
 from oracle_api import FAST, FAST_CF
+from parity_cases import corpus, sha
 
 pytestmark = pytest.mark.gpu
 
 
-def corpus(kind, size, seed):
-    from llmtokenizer_b200 import _lib
-    lib = _lib.load_corpus()
-    buf = np.zeros(size, dtype=np.uint8)
-    assert lib.gen_corpus_fill(kind, buf.ctypes.data, size, seed, 50000 if kind == 0 else 65536) == 0
-    return buf
-
-
-def assert_same(engine, oracle, data, cap=0, n_gpus=1, what=""):
+def expected_inline(oracle, data, cap=0):
     rc, om, ot, ost = oracle.train(data, cap, FAST_CF)
     assert rc == 0
-    m, t, st = engine.train(data, max_merges=cap, n_gpus=n_gpus)
+    return {"merges": om, "n_ids": len(ot), "ids_sha256": sha(ot), "same_bucket_ties": ost["same_bucket_ties"],
+            "threshold_edges": ost["threshold_edges"], "thread_buckets": ost["thread_buckets"]}
+
+
+def check_result(exp, m, t, st, n_gpus=1, what=""):
+    om = exp["merges"]
     k = min(len(m), len(om))
     first_bad = next((i for i in range(k) if tuple(m[i]) != tuple(om[i])), None)
     assert first_bad is None and len(m) == len(om), (
         f"{what}: merge lists differ (engine {len(m)} merges, oracle {len(om)}, first mismatch at {first_bad}: "
         f"engine {m[first_bad].tolist() if first_bad is not None else None} oracle "
-        f"{om[first_bad].tolist() if first_bad is not None else None}); engine stats {st}; oracle stats {ost}")
-    assert np.array_equal(t, ot), f"{what}: ids differ; engine stats {st}"
+        f"{om[first_bad].tolist() if first_bad is not None else None}); engine stats {st}")
+    assert len(t) == exp["n_ids"] and sha(t) == exp["ids_sha256"], f"{what}: ids differ; engine stats {st}"
     if n_gpus == 1:
         # the emulated bucket counts of the reference's 16 worker tables must track the oracle's exactly
-        assert st["worker_buckets"] == ost["thread_buckets"], (what, st["worker_buckets"], ost["thread_buckets"])
-        assert st["same_bucket_ties"] == ost["same_bucket_ties"] and st["threshold_edges"] == ost["threshold_edges"]
+        assert st["worker_buckets"] == list(exp["thread_buckets"]), (what, st["worker_buckets"], exp["thread_buckets"])
+        assert st["same_bucket_ties"] == exp["same_bucket_ties"] and st["threshold_edges"] == exp["threshold_edges"], (what, st)
+
+
+def assert_same(engine, oracle, data, cap=0, n_gpus=1, what=""):
+    """engine == oracle (run inline) on `data`"""
+    exp = expected_inline(oracle, data, cap)
+    m, t, st = engine.train(data, max_merges=cap, n_gpus=n_gpus)
+    check_result(exp, m, t, st, n_gpus, what)
     return m, t, st
+
+
+def assert_case(engine, oracle, key, n_gpus=1, options=None):
+    """engine == the oracle's committed result for parity_cases.TRAIN_CASES[key]"""
+    data, cap = pc.train_input(key)
+    exp = pc.expected_train(key, oracle)
+    if options:
+        ctx = engine.Context(0)
+        try:
+            for k, v in options.items():
+                ctx.set_option(k, v)
+            ctx.upload(data)
+            st = ctx.train(cap)
+            m, t = ctx.download()
+        finally:
+            ctx.close()
+    else:
+        m, t, st = engine.train(data, max_merges=cap, n_gpus=n_gpus)
+    check_result(exp, m, t, st, n_gpus, f"{key} P={n_gpus} {options or ''}")
+    return data, m, t, st
+
+
+def assert_encode_case(engine, oracle, key, m, n_gpus=1):
+    exp = pc.expected_encode(key, oracle)
+    ids, st = engine.encode(pc.ENCODE_CASES[key][1](), m, n_gpus=n_gpus)
+    assert len(ids) == exp["n_ids"] and sha(ids) == exp["ids_sha256"], (key, st)
+
+
+# ---- regressions first: inputs whose candidate list runs empty (round 1: the host loop span forever) ---------
+@pytest.mark.parametrize("n", [31, 62, 3839, 4000])
+def test_single_run_to_exhaustion(engine, oracle, n):
+    """b"a" * n: every merge halves the best count (3999, 1999, ... 30, 14), so a candidate list built for
+    "at least half the maximum" is empty after each merge (bpe.c:737-750 picks the new maximum every time)."""
+    assert_same(engine, oracle, np.full(n, 97, dtype=np.uint8), what=f"a*{n}")
+
+
+@pytest.mark.parametrize("symbols", [2, 3])
+def test_tiny_alphabets_to_exhaustion(engine, oracle, symbols):
+    rng = np.random.default_rng(100 + symbols)
+    for n in (40, 700, 3999, 20_000):
+        assert_same(engine, oracle, rng.integers(97, 97 + symbols, n, dtype=np.uint8), what=f"{symbols} symbols n={n}")
+    # long runs with rare breaks: counts fall steeply, lists are used up again and again
+    data = np.repeat(rng.integers(97, 97 + symbols, 400, dtype=np.uint8), rng.integers(1, 200, 400))
+    assert_same(engine, oracle, data, what=f"{symbols} symbols, long runs")
+
+
+def test_steep_counts_above_the_static_limit(engine, oracle):
+    """The same shapes in the streaming regime (>= 1,048,576 tokens): one long run, and a byte-level Zipf text
+    whose first merges have a handful of pairs above half the maximum (lists that run empty, thresholds that
+    are lowered a quarter at a time)."""
+    assert_same(engine, oracle, np.full(2_500_000, 97, dtype=np.uint8), what="a*2.5M")
+    assert_case(engine, oracle, "zipfb3m_1500")
+    assert_case(engine, oracle, "zipfb3m_1500", options={"batch_max": 1})
+
+
+def test_crossing_the_static_limit_inside_batched_passes(engine, oracle):
+    """1.4 M tokens that fall below 1,048,576 (where the reference starts slicing statically, bpe.c:449) while
+    merges share passes: the crossing iteration must be selected on its own so that the 16 worker tables' bucket
+    counts (compared by check_result) follow the oracle's.  The low histogram limit turns batching on from id 260."""
+    assert_case(engine, oracle, "cross1m_400", options={"smem_hist_max_vocab": 260, "batch_min_z": 260})
+    assert_case(engine, oracle, "cross1m_400")
+
+
+def test_tie_heavy_text_to_exhaustion(engine, oracle):
+    """60 shifted copies of a 20 KB random text (1.2 M tokens), to exhaustion: 15,104 merges, 419 of them decided
+    by the chain order inside one bucket (hash_table.c:208-223,300-302), above and below the static limit."""
+    _, _, _, st = assert_case(engine, oracle, "ties1m2_exh")
+    assert st["same_bucket_ties"] == 419
 
 
 @pytest.mark.parametrize("name", oracle_api.golden_names())
@@ -80,11 +158,9 @@ def test_tile_boundaries_and_runs(engine, oracle, n):
 
 
 def test_medium_corpora_capped(engine, oracle):
-    assert_same(engine, oracle, corpus(0, 6_000_000, 99), cap=300, what="zipf_ascii 6 MB / 300 merges")
-    assert_same(engine, oracle, corpus(1, 5_000_000, 98), cap=150, what="zipf_bytes 5 MB / 150 merges")
-    rt = oracle_api.golden("rt_full_cap300")["input"]
-    big = np.concatenate([rt, rt[::-1], rt[:300000]])      # 2.4 M tokens, dynamic regime throughout
-    assert_same(engine, oracle, big, cap=120, what="2.4 MB random text / 120 merges")
+    assert_case(engine, oracle, "zipfa6m_300")      # zipf_ascii 6 MB / 300 merges
+    assert_case(engine, oracle, "zipfb5m_150")      # zipf_bytes 5 MB / 150 merges
+    assert_case(engine, oracle, "rt2p4m_120")       # 2.4 MB random text, dynamic regime throughout / 120 merges
 
 
 @pytest.mark.parametrize("ranges", [1, 5, 64, 0])
@@ -114,9 +190,9 @@ def test_ranged_stream_boundaries(engine, oracle, ranges):
 def test_batched_passes_long_runs(engine, oracle):
     """Late in training most passes carry several provably-next merges (batched passes).  Long
     capped runs on corpora that stay above 1,048,576 tokens: the merge ORDER (ids) must be the sequential one."""
-    for kind, size, seed, cap in ((0, 12_000_000, 71, 2500), (1, 8_000_000, 72, 2200), (0, 9_000_000, 73, 2000)):
-        data = corpus(kind, size, seed)
-        m, t, st = assert_same(engine, oracle, data, cap=cap, what=f"kind {kind} {size} B / {cap} merges")
+    for key, kind in (("zipfa12m_2500", 0), ("zipfb8m_2200", 1), ("zipfa9m_2000", 0)):
+        data, m, t, st = assert_case(engine, oracle, key)
+        cap = len(m)
         if kind == 0:   # (merges share passes once the ids have outgrown the shared-memory delta histogram)
             assert st["batch_merges"] > 0 and st["replace_passes"] < cap, st
         # and with batching off the very same result
@@ -130,9 +206,7 @@ def test_batched_passes_long_runs(engine, oracle):
         # encoding batches consecutive ranks with unconnected tokens: same ids as training, and as the oracle elsewhere
         ids, se = engine.encode(data, m)
         assert np.array_equal(ids, t), se
-        other = corpus(kind, 3_000_000, seed + 100)
-        ids2, _ = engine.encode(other, m)
-        assert np.array_equal(ids2, oracle.encode(other, m))
+        assert_encode_case(engine, oracle, "enc_" + key, m)
 
 
 def test_batched_passes_beyond_the_class_table(engine, oracle):
@@ -141,8 +215,9 @@ def test_batched_passes_beyond_the_class_table(engine, oracle):
     alias each other may not share a pass.  10,000 merges on a stream that stays above 1,048,576 tokens;
     checked against the unbatched engine and against the oracle's committed digests; the oracle also checks
     the encoder on a smaller text and the decoder closes the loop."""
-    data = corpus(0, 12_000_000, 11)
-    cap = 10_000
+    key = "zipfa12m_10000"
+    data, cap = pc.train_input(key)
+    exp = pc.expected_train(key, oracle)
     res = []
     for bm in (8, 1):
         ctx = engine.Context(0)
@@ -153,31 +228,20 @@ def test_batched_passes_beyond_the_class_table(engine, oracle):
         if bm == 8:
             assert st["batch_merges"] > 0 and ctx.decode(m, download=False) == data.size and ctx.decode_mismatches() == 0
         ctx.close()
+        check_result(exp, m, t, st, 1, f"{key} batch_max {bm}")
         res.append((m, t, st))
     (m, t, st), (m1, t1, s1) = res
     assert len(m) == cap and s1["batch_merges"] == 0
-    assert np.array_equal(m, m1) and np.array_equal(t, t1), st
-    # and the oracle itself (three minutes of CPU: committed as digests, tools/make_c2_golden.py zipf12m_10k ...)
-    import hashlib
-    import json
-    import os
-    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "zipf12m_10k.json")))
-    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a, dtype="<u4").tobytes()).hexdigest()
-    assert (g["corpus"]["bytes"], g["corpus"]["seed"], g["merges"]) == (data.size, 11, cap)
-    assert len(t) == g["n_ids"] and sha(m) == g["merges_sha256"] and sha(t) == g["ids_sha256"]
     ids, se = engine.encode(data, m)
     assert np.array_equal(ids, t) and se["batch_merges"] > 0, se
-    other = corpus(0, 400_000, 12)
-    assert np.array_equal(engine.encode(other, m)[0], oracle.encode(other, m))
+    assert_encode_case(engine, oracle, "enc_" + key, m)
 
 
 def test_batched_passes_with_many_ties(engine, oracle):
     """Nearly uniform symbols: late merges all have almost the same count, so the order inside and between
     batches is decided by the bucket order again and again (and now and then by a same-bucket tie, which
     must end a batch and go through the exact resolver)."""
-    rng = np.random.default_rng(4)
-    data = rng.integers(33, 127, 14_000_000, dtype=np.uint8)
-    m, t, st = assert_same(engine, oracle, data, cap=2600, what="uniform 94 symbols, 14 MB / 2600 merges")
+    _, m, t, st = assert_case(engine, oracle, "uniform14m_2600")
     assert st["replace_passes"] <= 2600
 
 
@@ -229,24 +293,18 @@ def test_sharded_training_and_encoding_match_oracle(engine, oracle, P):
     exactly the single-stream result: merges, ids, any P."""
     if _device_count() < P:
         pytest.skip(f"needs {P} GPUs")
-    assert_same(engine, oracle, corpus(0, 8_000_000, 7), cap=200, n_gpus=P, what=f"zipf_ascii 8 MB P={P}")
-    assert_same(engine, oracle, corpus(1, 6_000_000, 8), cap=100, n_gpus=P, what=f"zipf_bytes 6 MB P={P}")
+    assert_case(engine, oracle, "zipfa8m_200", n_gpus=P)
+    assert_case(engine, oracle, "zipfb6m_100", n_gpus=P)
     # long enough for merges to share passes (ids beyond the shared-memory histogram), all ranks deciding alike
-    _, _, st = assert_same(engine, oracle, corpus(0, 12_000_000, 71), cap=1300, n_gpus=P, what=f"zipf_ascii 12 MB P={P}")
+    _, _, _, st = assert_case(engine, oracle, "zipfa12m_1300", n_gpus=P)
     assert st["batch_merges"] > 0, st
     # long runs of equal bytes: a == b merges whose run parity crosses shard boundaries
-    rng = np.random.default_rng(P)
-    runs = np.repeat(rng.integers(97, 100, 400_000, dtype=np.uint8), rng.integers(1, 30, 400_000))[:4_000_001]
-    assert_same(engine, oracle, runs, cap=12, n_gpus=P, what=f"runs P={P}")
-    same = np.full(3_000_003, 120, dtype=np.uint8)
-    assert_same(engine, oracle, same, cap=1, n_gpus=P, what=f"single run P={P}")
-    data = corpus(0, 3_000_000, 9)
-    m, t, _ = engine.train(data, max_merges=300)
+    assert_case(engine, oracle, f"runs4m_12_P{P}", n_gpus=P)
+    assert_case(engine, oracle, "same3m_1", n_gpus=P)
+    data, m, t, _ = assert_case(engine, oracle, "zipfa3m_300")
     ids, _ = engine.encode(data, m, n_gpus=P)
     assert np.array_equal(ids, t)
-    other = corpus(0, 2_000_001, 10)
-    ids2, _ = engine.encode(other, m, n_gpus=P)
-    assert np.array_equal(ids2, oracle.encode(other, m))
+    assert_encode_case(engine, oracle, "enc_zipfa3m_300", m, n_gpus=P)
 
 
 def test_config2_full_size_matches_the_oracle_digest(engine):
