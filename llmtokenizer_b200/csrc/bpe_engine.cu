@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -134,7 +135,7 @@ struct bpe_cuda_ctx
     u32 *d_pdesc = nullptr;
     size_t desc_cap = 0;
     // delta vectors (+ edge-record header)
-    int32_t *d_delta = nullptr, *d_delta_red = nullptr;
+    int32_t *d_delta = nullptr;
     size_t delta_cap = 0;
     // pair table (+ per-segment maxima of the hierarchical argmax)
     u64 *d_tkey = nullptr, *d_tmeta = nullptr;
@@ -192,9 +193,17 @@ struct bpe_cuda_ctx
     u32 *d_tile_cnt = nullptr;
     u64 *d_tile_off = nullptr;
     size_t tile_cap = 0;
-    // communicator
+    // communicator (bootstrap + the two collectives of a run's start) and the peer-memory exchange (struct Xchg)
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
+    Xchg hx{};                        // host copy of the exchange descriptor (goes into DevState at the start of a run)
+    u32 xseq = 0;                     // exchanges completed so far (continues from run to run: the flags are never reset)
+    size_t xcap_opt = 0;              // test knob: initial entries per inbox slot
+    u64 x_timeout_ms = 20000;         // BPE_CUDA_XCHG_TIMEOUT_MS
+    void *d_hello = nullptr;          // staging of the handle exchange
+    std::vector<void *> x_owned;      // every inbox this context ever allocated (freed with the context: a peer may still
+                                      // have an old one mapped)
+    std::vector<void *> x_mapped;     // peers' inboxes opened through CUDA IPC
     // options
     int profile_replace = 0;
     int batch_steps = 64;
@@ -216,17 +225,11 @@ struct bpe_cuda_ctx
 };
 
 static inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
-// One GPU: up to BATCH_MAX.  Several GPUs: the all-reduce carries one block of delta vectors per merge of a batch,
-// so batches are used (and kept to 4) only while the vocabulary is small (decided once per run from the merge cap,
-// identically on every rank).
+// Merges that may share one pass (the exchange between GPUs carries the touched counters only, so its cost does not
+// depend on the batch size or the vocabulary: the same limit for every world size).
 static inline size_t eff_batch(const bpe_cuda_ctx *c)
 {
-    const int bm = std::max(1, std::min(c->batch_max, (int)BATCH_MAX));
-    if (c->world == 1)
-        return (size_t)bm;
-    if (c->run_encode)
-        return 1;
-    return (c->run_max_merges != 0 && c->run_max_merges <= 8192 - 256) ? (size_t)std::min(bm, 4) : 1;
+    return (size_t)std::max(1, std::min(c->batch_max, (int)BATCH_MAX));
 }
 
 struct HostTimer
@@ -295,29 +298,122 @@ static int ensure_delta(bpe_cuda_ctx *c, size_t vocab)
     size_t cap = c->delta_cap ? c->delta_cap : (size_t)HDR_INTS + 4 * 8192;
     while (cap < need)
         cap *= 2;
-    // the vectors are all-zero between steps and the stream is idle when this is called; the
-    // header (edge records) must survive
-    int32_t *nd = nullptr, *nr = nullptr;
+    // the vectors are all-zero between steps and the stream is idle when this is called
+    int32_t *nd = nullptr;
     CU(cudaMalloc(&nd, cap * sizeof(int32_t)));
     CU(cudaMemsetAsync(nd, 0, cap * sizeof(int32_t), c->stream));
-    if (c->d_delta)
-        CU(cudaMemcpyAsync(nd, c->d_delta, HDR_INTS * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
-    if (c->world > 1)
-    {
-        CU(cudaMalloc(&nr, cap * sizeof(int32_t)));
-        CU(cudaMemsetAsync(nr, 0, cap * sizeof(int32_t), c->stream));
-        if (c->d_delta_red)
-            CU(cudaMemcpyAsync(nr, c->d_delta_red, HDR_INTS * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
-    }
     CU(cudaStreamSynchronize(c->stream));
     if (c->d_delta)
         CU(cudaFree(c->d_delta));
-    if (c->d_delta_red && c->d_delta_red != c->d_delta)
-        CU(cudaFree(c->d_delta_red));
     c->d_delta = nd;
-    c->d_delta_red = (c->world > 1) ? nr : nd;
     c->delta_cap = cap;
     return 0;
+}
+
+// ---- peer-memory exchange: inbox allocation and the handle exchange (struct Xchg in bpe_kernels.cuh) ------------
+// 256 Ki entries per (parity, sender) slot = 32 MB per rank; grown (ensure_xchg) when a pass could touch more counters
+constexpr size_t XCAP_DEFAULT = 1u << 18;
+struct XchgHello
+{
+    unsigned long long pid, ptr, xcap;
+    int device, pad;
+    cudaIpcMemHandle_t handle;
+};
+
+// Allocate an inbox of `xcap` entries per slot and learn every peer's.  Called by all ranks at the same point of
+// their (replicated) host logic with their streams drained: from set_comm, and from ensure_xchg when the lists may
+// outgrow the slots.  Ranks of one process (bpe_cuda_train with n_gpus > 1: one thread per GPU) use each other's
+// pointers directly with peer access enabled; ranks in separate processes (one per GPU, e.g. under torchrun) map
+// each other's inbox through CUDA IPC.  The handles travel through one ncclAllGather (bootstrap, not data path).
+static int xchg_setup(bpe_cuda_ctx *c, size_t xcap)
+{
+    CU(cudaSetDevice(c->device));
+    void *buf = nullptr;
+    CU(cudaMalloc(&buf, xchg_bytes(xcap)));
+    c->x_owned.push_back(buf);
+    CU(cudaMemsetAsync(buf, 0, xchg_bytes(xcap), c->stream));
+    if (c->hx.local) // flags, counts and edge records of the exchanges so far stay valid
+        CU(cudaMemcpyAsync(buf, c->hx.local, XCHG_HDR_WORDS * sizeof(u32), cudaMemcpyDeviceToDevice, c->stream));
+    XchgHello mine;
+    memset(&mine, 0, sizeof mine);
+    mine.pid = (unsigned long long)getpid();
+    mine.ptr = (unsigned long long)buf;
+    mine.xcap = xcap;
+    mine.device = c->device;
+    CU(cudaIpcGetMemHandle(&mine.handle, buf));
+    if (!c->d_hello)
+        CU(cudaMalloc(&c->d_hello, MAX_RANKS * sizeof(XchgHello)));
+    char *hello = static_cast<char *>(c->d_hello);
+    CU(cudaMemcpyAsync(hello + (size_t)c->rank * sizeof mine, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllGather(hello + (size_t)c->rank * sizeof mine, hello, sizeof mine, ncclChar, c->comm, c->stream));
+    std::vector<XchgHello> all((size_t)c->world);
+    CU(cudaMemcpyAsync(all.data(), hello, (size_t)c->world * sizeof mine, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    Xchg nx{};
+    nx.local = static_cast<u32 *>(buf);
+    nx.xcap = xcap;
+    for (int r = 0; r < c->world; r++)
+    {
+        const XchgHello &h = all[(size_t)r];
+        if (h.xcap != xcap)
+        {
+            set_error("exchange setup: rank %d allocated %llu entries per slot, rank %d %zu (ranks out of step)", r, h.xcap, c->rank, xcap);
+            return BPE_CUDA_ERR_STATE;
+        }
+        if (r == c->rank)
+            nx.peer[r] = nx.local;
+        else if (h.pid == mine.pid)
+        {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, c->device, h.device));
+            if (!can)
+            {
+                set_error("device %d cannot access device %d's memory (no NVLink / PCIe peer path)", c->device, h.device);
+                return BPE_CUDA_ERR_CUDA;
+            }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+            {
+                set_error("cudaDeviceEnablePeerAccess(%d) from device %d: %s", h.device, c->device, cudaGetErrorString(e));
+                return BPE_CUDA_ERR_CUDA;
+            }
+            cudaGetLastError();
+            nx.peer[r] = reinterpret_cast<u32 *>(h.ptr);
+        }
+        else
+        {
+            void *p = nullptr;
+            CU(cudaIpcOpenMemHandle(&p, h.handle, cudaIpcMemLazyEnablePeerAccess));
+            c->x_mapped.push_back(p);
+            nx.peer[r] = static_cast<u32 *>(p);
+        }
+    }
+    c->hx = nx;
+    // (a run in progress reads the descriptor from its control block)
+    CU(cudaMemcpyAsync(&c->d_st->x, &c->hx, sizeof(Xchg), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// Entries one pass can put into a slot: a counter per (merge of the batch, vector, token id), and no more than four
+// per replacement - the best count never grows, so `freq_bound` (the count of the last committed
+// merge, 0 = unknown) bounds every later merge's replacements.  Every rank calls this with the same arguments.
+static int ensure_xchg(bpe_cuda_ctx *c, size_t z_ub, u64 freq_bound)
+{
+    if (c->world <= 1)
+        return 0;
+    const size_t bm = eff_batch(c);
+    size_t need = bm * 4 * (z_ub + bm + 1);
+    if (freq_bound)
+        need = (size_t)std::min<u64>(need, 4ull * bm * freq_bound);
+    if (need <= c->hx.xcap)
+        return 0;
+    size_t cap = (size_t)c->hx.xcap;
+    while (cap < need)
+        cap *= 2;
+    if (c->debug)
+        fprintf(stderr, "[bpe_cuda r%d] exchange inbox grows to %zu entries per slot\n", c->rank, cap);
+    return xchg_setup(c, cap);
 }
 
 static int ensure_logs(bpe_cuda_ctx *c, size_t merges)
@@ -444,7 +540,7 @@ static int check_state(bpe_cuda_ctx *c)
                 c->h_st->cand_T, c->h_st->ncand);
     if (c->h_st->err)
     {
-        set_error("device reported error flags 0x%x (1=table full 2=missing key 4=negative count 8=probe/logic)", c->h_st->err);
+        set_error("device reported error flags 0x%x (1=table full 2=missing key 4=negative count 8=probe/logic 16=exchange slot overflow 32=peer flag timeout)", c->h_st->err);
         return BPE_CUDA_ERR_STATE;
     }
     return 0;
@@ -673,11 +769,11 @@ static int choose_candidates(bpe_cuda_ctx *c, u32 best)
 static int enqueue_select(bpe_cuda_ctx *c, bool encode)
 {
     if (encode)
-        apply_select_kernel<<<2, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_delta_red, c->d_delta, 1);
+        apply_select_kernel<<<2, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_delta, AS_ENCODE);
     else if (c->cand_T == 0)
-        select_kernel<<<c->sel_grid, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_part, c->d_delta_red);
+        select_kernel<<<c->sel_grid, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_part);
     else
-        apply_select_kernel<<<2, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_delta_red, c->d_delta, 0);
+        apply_select_kernel<<<2, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_delta, AS_TRAIN);
     c->launches++;
     return 0;
 }
@@ -727,30 +823,27 @@ static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool c
     prof_mark(c, PT_REPLACE);
     c->launches++;
     c->stats.replace_launches++;
-    if (c->world > 1)
-    {
-        edge_record_kernel<<<1, 32, 0, c->stream>>>(c->d_st, c->d_delta, 1);
-        c->launches++;
-        // (the device may be ahead of the host's id estimate when merges share passes: reduce up to the bound)
-        const size_t words = std::min(delta_need(c, (size_t)z_ub), c->delta_cap);
-        NC(g_nccl.AllReduce(c->d_delta, c->d_delta_red, words, ncclInt32, ncclSum, c->comm, c->stream));
-    }
+    // every thread looks at one token's four counters (128 bits) per trip; 32 blocks keep the "last block" wait short
+    // (batches are mostly short: size the grid for two merges, the loop is grid-stride).  Several GPUs: the same
+    // launch pushes this rank's touched counters into the peers' inboxes and folds theirs in (struct Xchg).
+    const int agrid = (int)std::min<u64>((std::min<u64>(eff_batch(c), 2) * 4ull * (z + 1) + SEL_THREADS - 1) / SEL_THREADS, 64);
     if (encode || c->cand_T)
     {
-        // one GPU: apply walks the list of touched counters (a few thousand); several: the dense all-reduced vectors
-        // every thread looks at one token's four counters (128 bits) per trip; 32 blocks keep the "last block" wait short
-        // (batches are mostly short: size the grid for two merges, the loop is grid-stride)
-        const int agrid = (int)std::min<u64>((std::min<u64>(eff_batch(c), 2) * 4ull * (z + 1) + SEL_THREADS - 1) / SEL_THREADS, 64);
-        CU(launch_chained(c, apply_select_kernel, agrid + 1, SEL_THREADS, 0, c->d_st, c->d_delta_red, c->d_delta, encode ? 1 : 0));
+        CU(launch_chained(c, apply_select_kernel, agrid + 1, SEL_THREADS, 0, c->d_st, c->d_delta, encode ? (int)AS_ENCODE : (int)AS_TRAIN));
         c->launches++;
         prof_mark(c, PT_APPLY);
     }
     else
     {
-        const int agrid = (int)std::min<u64>((4ull * (z + 1) + 255) / 256, (u64)c->sm_count * 4);
-        apply_kernel<<<agrid, 256, 0, c->stream>>>(c->d_st, c->d_delta_red, c->d_delta);
+        if (c->world > 1)
+            CU(launch_chained(c, apply_select_kernel, agrid + 1, SEL_THREADS, 0, c->d_st, c->d_delta, (int)AS_APPLY_ONLY));
+        else
+        {
+            const int g1 = (int)std::min<u64>((4ull * (z + 1) + 255) / 256, (u64)c->sm_count * 4);
+            apply_kernel<<<g1, 256, 0, c->stream>>>(c->d_st, c->d_delta);
+        }
         prof_mark(c, PT_APPLY);
-        select_kernel<<<c->sel_grid, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_part, c->d_delta_red);
+        select_kernel<<<c->sel_grid, SEL_THREADS, 0, c->stream>>>(c->d_st, c->d_part);
         c->launches += 2;
         prof_mark(c, PT_SELECT);
     }
@@ -909,6 +1002,8 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
         const u64 batch = (u64)std::max(1, c->batch_steps);
         if ((rc = ensure_delta(c, (size_t)(X.z0 + 3 * batch * bm + 4))))
             return rc;
+        if ((rc = ensure_xchg(c, (size_t)(X.z0 + 3 * batch * bm + 4), (!encode && h->merges_done) ? h->freq : 0)))
+            return rc;
         if ((rc = ensure_logs(c, (size_t)(X.m1 + 3 * batch * bm + 4))))
             return rc;
         u64 z_ub = X.z0 + X.G * bm, m_ub = X.m1 + X.G * bm; // how far the device may have got when X is done
@@ -1050,6 +1145,9 @@ static int init_state(bpe_cuda_ctx *c, u64 n_local, u64 max_merges, bool encode,
     s.halo_after[0] = s.halo_after[1] = s.halo_after[2] = SENT;
     s.rank = (u32)c->rank;
     s.world = (u32)c->world;
+    s.x = c->hx;
+    s.xseq = c->xseq;
+    s.x_timeout_ns = c->x_timeout_ms * 1000000ull;
     for (int t = 0; t < REF_THREADS; t++)
         s.bt[t] = 256; // bpe.c:610,615
     s.merges = c->d_merges;
@@ -1146,8 +1244,6 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
     if ((rc = ensure_delta(c, 8192)))
         return rc;
     CU(cudaMemsetAsync(c->d_delta, 0, c->delta_cap * sizeof(int32_t), c->stream));
-    if (c->world > 1)
-        CU(cudaMemsetAsync(c->d_delta_red, 0, c->delta_cap * sizeof(int32_t), c->stream));
     CU(cudaMemsetAsync(c->d_desc, 0, c->desc_cap * sizeof(u64), c->stream));
     CU(cudaMemsetAsync(c->d_pdesc, 0, c->desc_cap * sizeof(u32), c->stream));
     CU(cudaMemsetAsync(c->d_dense, 0, 65536 * sizeof(u32), c->stream));
@@ -1176,9 +1272,11 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
     }
     if (c->world > 1)
     {
-        edge_record_kernel<<<1, 32, 0, c->stream>>>(c->d_st, c->d_delta, 0);
-        NC(g_nccl.AllReduce(c->d_delta, c->d_delta_red, HDR_INTS, ncclInt32, ncclSum, c->comm, c->stream));
-        resolve_edges_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_delta_red);
+        // every rank's edge record (one exchange over peer memory), this rank's halos, the byte pair that straddles
+        // the shard boundary (counted by the left shard), and the one real collective of a run: the sum of the dense
+        // 256 x 256 byte-pair histograms
+        edge_exchange_kernel<<<1, 32, 0, c->stream>>>(c->d_st, 0);
+        resolve_edges_kernel<<<1, 1, 0, c->stream>>>(c->d_st);
         boundary_pair_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_dense);
         NC(g_nccl.AllReduce(c->d_dense, c->d_dense, 65536, ncclUint32, ncclSum, c->comm, c->stream));
         c->launches += 3;
@@ -1194,9 +1292,10 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
         u64 n_global = c->h_st->n_global;
         if (c->world > 1)
         {
-            // header of the reduced buffer holds every rank's length
+            // the records of the exchange that has just completed hold every rank's length
             std::vector<u32> hdr(HDR_INTS);
-            CU(cudaMemcpyAsync(hdr.data(), c->d_delta_red, HDR_INTS * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaMemcpyAsync(hdr.data(), c->hx.local + XCHG_RECS + (c->h_st->xseq & 1u) * MAX_RANKS * REC_INTS,
+                               HDR_INTS * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
             CU(cudaStreamSynchronize(c->stream));
             n_global = 0;
             for (int r = 0; r < c->world; r++)
@@ -1227,6 +1326,7 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
     CU(cudaEventDestroy(ev1));
 
     DevState *h = c->h_st;
+    c->xseq = h->xseq;
     if (c->debug)
         fprintf(stderr, "[bpe_cuda] host ms: rehash %.1f | candidates %.1f | pauses %.1f | poll waits %.1f | enqueue %.1f\n", c->host_ms[0],
                 c->host_ms[1], c->host_ms[2], c->host_ms[3], c->host_ms[4]);
@@ -1313,14 +1413,13 @@ __global__ void tie_min_key_kernel(DevState *st)
             atomicMin(&st->probe_key, st->tkey[i]);
     }
 }
-__global__ void tier_a_commit_kernel(DevState *st, const int32_t *delta_reduced)
+__global__ void tier_a_commit_kernel(DevState *st)
 {
     // sharded stream: among the pairs that tie inside the winning bucket, the smallest pair key (same on every rank)
     if (st->stop != STOP_PAUSE)
         return;
     const u64 key = st->probe_key != ~0ull ? st->probe_key : st->tkey[st->sel_slot];
-    commit_merge(st, (u32)(key & 0xFFFFFFFFull), (u32)(key >> 32), (u32)(st->sel_key >> 32),
-                 reinterpret_cast<const u32 *>(delta_reduced));
+    commit_merge(st, (u32)(key & 0xFFFFFFFFull), (u32)(key >> 32), (u32)(st->sel_key >> 32), cur_recs(st));
     st->stop = STOP_RUN;
     st->pause = 0;
 }
@@ -1364,6 +1463,8 @@ static int resolve_pause(bpe_cuda_ctx *c, bool encode)
         c->launches++;
         if ((rc = ensure_delta(c, (size_t)(256 + merges_done + 2))))
             return rc;
+        if ((rc = ensure_xchg(c, (size_t)(256 + merges_done + 2), 0)))
+            return rc;
         if ((rc = ensure_logs(c, (size_t)(merges_done + 2))))
             return rc;
         return enqueue_step(c, (u32)(256 + merges_done - 1), n, encode, false, false);
@@ -1378,6 +1479,8 @@ static int resolve_pause(bpe_cuda_ctx *c, bool encode)
     c->stats.resolver_runs++;
     if ((rc = ensure_delta(c, (size_t)(256 + merges_done + 2))))
         return rc;
+    if ((rc = ensure_xchg(c, (size_t)(256 + merges_done + 2), 0)))
+        return rc;
     if ((rc = ensure_logs(c, (size_t)(merges_done + 2))))
         return rc;
     if (c->world > 1)
@@ -1386,7 +1489,7 @@ static int resolve_pause(bpe_cuda_ctx *c, bool encode)
         // (the smallest pair key among the tied pairs: slot numbers differ from rank to rank, pair keys do not)
         tie_reset_kernel<<<1, 1, 0, c->stream>>>(c->d_st);
         tie_min_key_kernel<<<(int)std::min<u64>((c->tcap + 255) / 256, (u64)c->sm_count * 8), 256, 0, c->stream>>>(c->d_st);
-        tier_a_commit_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_delta_red);
+        tier_a_commit_kernel<<<1, 1, 0, c->stream>>>(c->d_st);
         c->launches += 3;
         return enqueue_step(c, (u32)(256 + merges_done), n, encode, false, false);
     }
@@ -1406,7 +1509,7 @@ static int resolve_pause(bpe_cuda_ctx *c, bool encode)
     cand_bucket_kernel<<<sg, 256, 0, c->stream>>>(c->d_st, c->d_rs);
     cand_collect_kernel<<<sg, 256, 0, c->stream>>>(c->d_st, c->d_rs, c->d_first, c->d_rank);
     entry_pass2_kernel<<<g, 256, 0, c->stream>>>(c->d_st, c->d_rs, c->d_first, c->d_pos_slot, c->d_rank);
-    resolver_commit_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_rs, c->d_delta_red);
+    resolver_commit_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_rs);
     c->launches += 9;
     CU(cudaGetLastError());
     return enqueue_step(c, (u32)(256 + merges_done), n, encode, false, false);
@@ -1509,6 +1612,10 @@ int bpe_cuda_ctx_create(int device, bpe_cuda_ctx_t **out)
         c->pdl = atoi(e) != 0;
     if (const char *e = getenv("BPE_CUDA_SPECULATE"))
         c->speculate = atoi(e) != 0;
+    if (const char *e = getenv("BPE_CUDA_XCHG_TIMEOUT_MS"))
+        c->x_timeout_ms = (u64)std::max(1, atoi(e));
+    if (const char *e = getenv("BPE_CUDA_XCHG_CAP"))
+        c->xcap_opt = (size_t)std::max(64, atoi(e));
     *out = c;
     return 0;
 }
@@ -1542,8 +1649,11 @@ void bpe_cuda_ctx_destroy(bpe_cuda_ctx_t *c)
         cudaFree(c->d_redge[i]);
     }
     cudaFree(c->d_delta);
-    if (c->d_delta_red != c->d_delta)
-        cudaFree(c->d_delta_red);
+    cudaFree(c->d_hello);
+    for (void *p : c->x_mapped)
+        cudaIpcCloseMemHandle(p);
+    for (void *p : c->x_owned)
+        cudaFree(p);
     table_free(c);
     cudaFree(c->d_part);
     cudaFree(c->d_cand);
@@ -1601,14 +1711,7 @@ int bpe_cuda_ctx_set_comm(bpe_cuda_ctx_t *c, int rank, int world, const void *id
     NC(g_nccl.CommInitRank(&c->comm, world, id, rank));
     c->rank = rank;
     c->world = world;
-    // the reduced-delta buffer becomes a separate allocation
-    if (c->d_delta)
-    {
-        cudaFree(c->d_delta);
-        c->d_delta = c->d_delta_red = nullptr;
-        c->delta_cap = 0;
-    }
-    return 0;
+    return xchg_setup(c, c->xcap_opt ? c->xcap_opt : XCAP_DEFAULT);
 }
 
 int bpe_cuda_ctx_upload(bpe_cuda_ctx_t *c, const uint8_t *shard, size_t n)
@@ -1724,6 +1827,8 @@ int bpe_cuda_ctx_set_option(bpe_cuda_ctx_t *c, const char *name, long long value
         c->speculate = (int)(value != 0);
     else if (!strcmp(name, "use_stream"))
         c->use_stream = (int)(value != 0);
+    else if (!strcmp(name, "xchg_cap")) // entries per inbox slot at set_comm (test knob: small values force growth)
+        c->xcap_opt = (size_t)std::max<long long>(64, value);
     else
         return BPE_CUDA_ERR_ARG;
     return 0;
@@ -1967,7 +2072,22 @@ struct RankJob
     char err[512];
 };
 
+static void rank_body(RankJob *j);
 static void rank_main(RankJob *j)
+{
+    // (a C++ exception escaping a thread would terminate the process)
+    try
+    {
+        rank_body(j);
+    }
+    catch (const std::exception &e)
+    {
+        j->rc = BPE_CUDA_ERR_NOMEM;
+        snprintf(j->err, sizeof j->err, "rank %d: %s", j->rank, e.what());
+    }
+}
+
+static void rank_body(RankJob *j)
 {
     bpe_cuda_ctx_t *c = nullptr;
     j->err[0] = 0;
@@ -2021,6 +2141,15 @@ static int run_host(const uint8_t *bytes, size_t n_in, uint64_t max_merges, cons
     {
         set_error("Error: File contains less than 2 characters");
         return BPE_CUDA_ERR_SHORT;
+    }
+    {
+        // a rank without a device would fail at once and leave its peers waiting in the communicator setup
+        const int ndev = bpe_cuda_device_count();
+        if (n_gpus > ndev)
+        {
+            set_error("n_gpus = %d but only %d CUDA device(s) are visible", n_gpus, ndev);
+            return BPE_CUDA_ERR_CUDA;
+        }
     }
     std::vector<RankJob> jobs((size_t)n_gpus);
     ncclUniqueId id;

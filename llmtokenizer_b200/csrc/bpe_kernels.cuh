@@ -65,8 +65,32 @@ enum : u32
     ERR_TABLE_FULL = 1,
     ERR_MISSING_KEY = 2,
     ERR_NEGATIVE = 4,
-    ERR_PROBE = 8
+    ERR_PROBE = 8,
+    ERR_XCHG_OVERFLOW = 16, // a rank's list of touched counters outgrew its slot in the peers' inboxes
+    ERR_XCHG_TIMEOUT = 32   // a peer's flag did not arrive (a rank died or fell out of step)
 };
+
+// Multi-GPU exchange over NVLink peer memory.  Every rank owns one INBOX buffer that all
+// peers can write: after a pass each rank pushes the pair-count deltas its shard produced - as a compact list
+// of (counter index, value) entries, a few thousand whatever the vocabulary size - and its pair-independent edge
+// record into its slot of every peer's inbox, then raises its flag there.  Every rank folds all P lists into
+// its replica of the pair table (integer adds commute, so all replicas end up identical); nothing is reduced
+// in between and no collective is launched.  Two parities: a rank can be at most one pass ahead of a peer.
+//   inbox layout (u32 words): flags[MAX_RANKS] | counts[2][MAX_RANKS] | recs[2][MAX_RANKS][REC_INTS] | pad to
+//   XCHG_HDR_WORDS | entries[2][MAX_RANKS][xcap] (u64: index | value << 32)
+constexpr u32 XCHG_FLAGS = 0, XCHG_COUNTS = 64, XCHG_RECS = 128, XCHG_HDR_WORDS = 256;
+struct Xchg
+{
+    u32 *local;             // my inbox
+    u32 *peer[MAX_RANKS];   // every rank's inbox as mapped into my address space (peer[rank] == local)
+    u64 xcap;               // entries per (parity, sender) slot
+};
+__host__ __device__ inline size_t xchg_bytes(u64 xcap) { return (size_t)XCHG_HDR_WORDS * 4 + (size_t)2 * MAX_RANKS * xcap * 8; }
+__device__ __forceinline__ u64 *xchg_entries(u32 *inbox, u64 xcap, u32 par, u32 sender)
+{
+    return reinterpret_cast<u64 *>(inbox + XCHG_HDR_WORDS) + ((u64)par * MAX_RANKS + sender) * xcap;
+}
+__device__ __forceinline__ u32 *xchg_recs(u32 *inbox, u32 par) { return inbox + XCHG_RECS + par * MAX_RANKS * REC_INTS; }
 
 // Device-resident control block.  Everything a merge step needs lives here, so a step is a fixed
 // sequence of launches with no host round trip.
@@ -134,6 +158,10 @@ struct DevState
     // shard edges (single GPU: SENT / 0)
     u32 halo_before[2], halo_after[3], carry_in;
     u32 rank, world;
+    // peer-memory exchange (world > 1): sequence number of the last exchange this rank completed, scratch counters
+    Xchg x;
+    u32 xseq, x_count, x_done, x_pad;
+    u64 x_timeout_ns; // how long a rank waits for a peer's flag before it stops the run with an error
     // the reference's 16 worker tables keep their grown bucket count across iterations
     u64 bt[REF_THREADS];
     // logs
@@ -147,7 +175,7 @@ struct DevState
 
 // ---------------------------------------------------------------------------------------------
 // hash_table.c:8-53 on the 8-byte key {u32 a; u32 b}
-__host__ // Programmatic dependent launch: a kernel launched with the "programmatic stream serialization" attribute may be
+// Programmatic dependent launch: a kernel launched with the "programmatic stream serialization" attribute may be
 // scheduled while its predecessor is still running; pdl_wait() blocks until the predecessor has completed and its
 // writes are visible (a no-op for a normal launch), pdl_launch_dependents() lets the successor's CTAs be scheduled.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -160,6 +188,27 @@ __device__ __forceinline__ u64 gtime()
     return t;
 }
 __host__ __device__ __forceinline__ u32 rotl32(u32 x, int r) { return (x << r) | (x >> (32 - r)); }
+
+// system-scope release / acquire on a flag another GPU reads / writes through NVLink peer memory
+__device__ __forceinline__ void st_release_sys(u32 *p, u32 v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ u32 ld_acquire_sys(const u32 *p)
+{
+    u32 v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ u64 ld_relaxed_sys_u64(const u64 *p)
+{
+    u64 v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ u32 ld_relaxed_sys_u32(const u32 *p)
+{
+    u32 v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 __host__ __device__ __forceinline__ u32 murmur3_pair(u32 a, u32 b)
 {
@@ -461,17 +510,14 @@ __global__ void table_swap_kernel(DevState *st, u64 *nkey, u64 *nmeta, u64 ncap,
 // all-reduce sums; disjoint slots make the sum an all-gather, so there is ONE collective per merge.
 //   rec[0..1] = length (lo, hi)   rec[2..4] = first tokens   rec[5..6] = last two tokens
 //   rec[7]    = trailing-run parity | uniform<<1
-__global__ void edge_record_kernel(DevState *st, int32_t *delta_local, int use_next)
+// (32 lanes; the record is complete in lane 0)
+__device__ inline void edge_record_compute(const DevState *st, bool nxt, u32 rec[REC_INTS])
 {
-    if (st->stop != STOP_RUN && use_next)
-        return;
-    const bool nxt = use_next && !st->skip;
     const u32 buf = nxt ? (st->cur ^ 1u) : st->cur;
     const u32 layout = nxt ? st->layout_next : st->layout;
     const u64 len = nxt ? st->n_next : st->n;
     const u32 *s = st->tok[buf];
-    const int lane = threadIdx.x;
-    u32 *rec = reinterpret_cast<u32 *>(delta_local) + st->rank * REC_INTS;
+    const int lane = threadIdx.x & 31;
     StreamEnds e;
     stream_ends(st, buf, layout, len, e);
     // trailing run of the last token, 32 tokens per step, range by range from the back
@@ -502,15 +548,82 @@ __global__ void edge_record_kernel(DevState *st, int32_t *delta_local, int use_n
         }
         uniform = (run == len);
     }
-    if (lane == 0)
+    rec[0] = (u32)len;
+    rec[1] = (u32)(len >> 32);
+    for (int k = 0; k < 3; k++)
+        rec[2 + k] = e.first[k];
+    rec[5] = e.last2[0];
+    rec[6] = e.last2[1];
+    rec[7] = (u32)(run & 1ull) | ((u32)uniform << 1);
+}
+
+// ---- peer-memory exchange primitives (see struct Xchg) ----------------------------------------------
+// the records every rank pushed in exchange `seq` (the latest one this rank completed: st->xseq)
+__device__ __forceinline__ const u32 *cur_recs(const DevState *st)
+{
+    return st->world > 1 ? xchg_recs(st->x.local, st->xseq & 1u) : nullptr;
+}
+// lane 0 of the calling warp: publish my record for exchange `seq` in every inbox (mine included)
+__device__ inline void xchg_push_record(DevState *st, u32 seq, const u32 rec[REC_INTS])
+{
+    for (u32 p = 0; p < st->world; p++)
     {
-        rec[0] = (u32)len;
-        rec[1] = (u32)(len >> 32);
-        for (int k = 0; k < 3; k++)
-            rec[2 + k] = e.first[k];
-        rec[5] = e.last2[0];
-        rec[6] = e.last2[1];
-        rec[7] = (u32)(run & 1ull) | ((u32)uniform << 1);
+        u32 *dst = xchg_recs(st->x.peer[p], seq & 1u) + st->rank * REC_INTS;
+        for (int k = 0; k < REC_INTS; k++)
+            dst[k] = rec[k];
+    }
+}
+// one thread, after every write of this rank for exchange `seq` is fenced: tell the peers how many entries my list
+// holds and raise my flag in their inboxes
+__device__ inline void xchg_signal(DevState *st, u32 seq, u32 count)
+{
+    for (u32 p = 0; p < st->world; p++)
+        if (p != st->rank)
+            st->x.peer[p][XCHG_COUNTS + (seq & 1u) * MAX_RANKS + st->rank] = count;
+    __threadfence_system();
+    for (u32 p = 0; p < st->world; p++)
+        if (p != st->rank)
+            st_release_sys(st->x.peer[p] + XCHG_FLAGS + st->rank, seq);
+}
+// one thread: wait until `sender` has raised its flag for exchange `seq` in my inbox.  Peers run the same launch
+// sequence on their own GPUs; a flag that does not arrive within x_timeout_ns (20 s) means a rank died or fell out of step:
+// the run is stopped with an error instead of spinning for ever.
+__device__ inline bool xchg_wait(DevState *st, u32 sender, u32 seq)
+{
+    const u32 *f = st->x.local + XCHG_FLAGS + sender;
+    const u64 t0 = gtime();
+    u32 spins = 0;
+    while ((int)(ld_acquire_sys(f) - seq) < 0)
+    {
+        if ((++spins & 1023u) == 0 && gtime() - t0 > st->x_timeout_ns)
+        {
+            atomicOr(&st->err, ERR_XCHG_TIMEOUT);
+            st->stop = STOP_ERROR;
+            return false;
+        }
+    }
+    return true;
+}
+
+// Exchange of the edge records alone (start of a run: nothing has been merged yet, or after the host changed the
+// stream).  One warp.  Afterwards every rank knows every shard's length and edge tokens.
+__global__ void edge_exchange_kernel(DevState *st, int use_next)
+{
+    if (st->world <= 1 || (st->stop != STOP_RUN && use_next))
+        return;
+    u32 rec[REC_INTS];
+    edge_record_compute(st, use_next && !st->skip, rec);
+    const u32 seq = st->xseq + 1u;
+    if (threadIdx.x == 0)
+    {
+        xchg_push_record(st, seq, rec);
+        __threadfence_system();
+        xchg_signal(st, seq, 0u);
+        bool ok = true;
+        for (u32 p = 0; p < st->world && ok; p++)
+            if (p != st->rank)
+                ok = xchg_wait(st, p, seq);
+        st->xseq = seq;
     }
 }
 
@@ -895,13 +1008,12 @@ __device__ inline void decide_list(DevState *st, u64 k, u64 s, u32 m, const PreD
 
 // The decision once the best packed key (count << 32 | ~bucket), its multiplicity and a slot holding
 // it are known: stop / pause / commit (bpe.c:730-758).  One thread.
-__device__ inline void decide(DevState *st, u64 k, u64 s, u32 m, const int32_t *delta_reduced, const PreDecide *pre = nullptr)
+__device__ inline void decide(DevState *st, u64 k, u64 s, u32 m, const u32 *rec_all, const PreDecide *pre = nullptr)
 {
     const u64 D = (u64)st->distinct;
     st->sel_key = k;
     st->sel_slot = s;
     st->sel_mult = m;
-    const u32 *rec_all = reinterpret_cast<const u32 *>(delta_reduced);
     if (st->world > 1)
     {
         u64 total = 0;
@@ -955,7 +1067,7 @@ __device__ inline void decide(DevState *st, u64 k, u64 s, u32 m, const int32_t *
 
 // encode: the "selection" is simply the next rank of the given merge list; a rank whose pair does
 // not occur (count 0 in the replicated table) costs no pass.  One thread.
-__device__ inline void decide_rank(DevState *st, const int32_t *delta_reduced)
+__device__ inline void decide_rank(DevState *st, const u32 *rec_all)
 {
     const u64 r = st->merges_done;
     if (r >= st->enc_total)
@@ -966,7 +1078,6 @@ __device__ inline void decide_rank(DevState *st, const int32_t *delta_reduced)
     const u32 a = st->enc_merges[2 * r], b = st->enc_merges[2 * r + 1];
     const u64 slot = table_find(st->tkey, st->tcap, (u64)a | ((u64)b << 32), murmur3_pair(a, b));
     const u32 cnt = (slot == NO_SLOT) ? 0u : *cnt_ptr(st->tmeta, slot);
-    const u32 *rec_all = reinterpret_cast<const u32 *>(delta_reduced);
     commit_merge(st, a, b, cnt, rec_all, true);
     if (cnt == 0)
         st->skip = 1;
@@ -1005,7 +1116,7 @@ __device__ inline void decide_rank(DevState *st, const int32_t *delta_reduced)
 }
 
 // K2, whole-table form (no candidate list: start of training, tiny counts near exhaustion).
-__global__ void __launch_bounds__(SEL_THREADS) select_kernel(DevState *st, SelPart *part, const int32_t *delta_reduced)
+__global__ void __launch_bounds__(SEL_THREADS) select_kernel(DevState *st, SelPart *part)
 {
     if (st->stop != STOP_RUN || st->pending)
         return;
@@ -1053,14 +1164,14 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(DevState *st, SelPa
     if (threadIdx.x != 0)
         return;
     st->sel_done = 0;
-    decide(st, k, s, m, delta_reduced);
+    decide(st, k, s, m, cur_recs(st));
 }
 
-__global__ void select_rank_kernel(DevState *st, const int32_t *delta_reduced)
+__global__ void select_rank_kernel(DevState *st)
 {
     if (st->stop != STOP_RUN || st->pending)
         return;
-    decide_rank(st, delta_reduced);
+    decide_rank(st, cur_recs(st));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1474,7 +1585,73 @@ __device__ __forceinline__ u64 table_insert_counted(DevState *st, u64 *tkey, u64
     return NO_SLOT;
 }
 
-__device__ inline void apply_deltas(DevState *st, int32_t *delta_in, int32_t *delta_local, u32 gtid, u32 gsize)
+// one delta counter -> the pair table.  Entry e of the delta vectors: merge i of the batch owns the block
+// [i * 4 * VS, (i + 1) * 4 * VS), VS = z + nb (one slot per token id that exists after the pass); inside a block,
+// token t holds {-(t,a_i), -(b_i,t), +(t,z_i), +(z_i,t)}
+__device__ __forceinline__ void apply_entry(DevState *st, u64 *tkey, u64 *tmeta, u64 cap, u32 e, int32_t d, u32 VS, u32 z0, int *s_dD,
+                                            int *s_occ)
+{
+    const u32 bi = e / (4 * VS), r = e - bi * 4 * VS;
+    const u32 a = st->ba[bi], b = st->bb[bi], z = z0 + bi;
+    const u32 t = r >> 2, vec = r & 3u;
+    u32 ka, kb;
+    if (vec == 0)
+    {
+        ka = t;
+        kb = a;
+    }
+    else if (vec == 1)
+    {
+        ka = b;
+        kb = t;
+    }
+    else if (vec == 2)
+    {
+        ka = t;
+        kb = z;
+    }
+    else
+    {
+        ka = z;
+        kb = t;
+    }
+    const u64 key = (u64)ka | ((u64)kb << 32);
+    const u32 h = murmur3_pair(ka, kb);
+    if (vec >= 2)
+    {
+        const u64 s = table_insert_counted(st, tkey, tmeta, cap, key, h, s_occ);
+        if (s == NO_SLOT)
+        {
+            atomicOr(&st->err, ERR_TABLE_FULL);
+            return;
+        }
+        const u32 old = atomicAdd(cnt_ptr(tmeta, s), (u32)d);
+        if (old == 0)
+            atomicAdd(s_dD, 1);
+        cand_offer(st, s, old + (u32)d);
+    }
+    else
+    {
+        const u64 s = table_find(tkey, cap, key, h);
+        if (s == NO_SLOT)
+        {
+            atomicOr(&st->err, ERR_MISSING_KEY);
+            return;
+        }
+        const u32 old = atomicSub(cnt_ptr(tmeta, s), (u32)d);
+        if (old < (u32)d)
+            atomicOr(&st->err, ERR_NEGATIVE);
+        if (old == (u32)d)
+            atomicAdd(s_dD, -1);
+    }
+}
+
+// This rank's own deltas: fold them into the table, clear them, and (several GPUs: `xch`) push every non-zero
+// counter as one (index, value) entry into my slot of every peer's inbox.  Integer adds commute, so every replica
+// of the table ends up with the sum over all ranks whatever order the lists are folded in; D is kept exact by the
+// 0 <-> non-0 transitions of the individual adds (a pass never adds to and subtracts from the same key: additions
+// go to pairs that contain a new id).
+__device__ inline void apply_deltas(DevState *st, int32_t *delta, u32 gtid, u32 gsize, bool xch, u32 xpar)
 {
     __shared__ int s_dD, s_occ;
     if (threadIdx.x == 0)
@@ -1483,8 +1660,6 @@ __device__ inline void apply_deltas(DevState *st, int32_t *delta_in, int32_t *de
         s_occ = 0;
     }
     __syncthreads();
-    // delta layout: merge i of the batch owns the block [i * 4 * VS, (i + 1) * 4 * VS), VS = z + nb (one slot per
-    // token id that exists after the pass); inside a block, token t holds {-(t,a_i), -(b_i,t), +(t,z_i), +(z_i,t)}
     const u32 nb = st->nb, z0 = st->z;
     const u32 VS = z0 + nb;
     const u32 total = nb * 4 * VS;
@@ -1503,69 +1678,82 @@ __device__ inline void apply_deltas(DevState *st, int32_t *delta_in, int32_t *de
                 atomicAdd(&s_dD, -1);
         }
     }
-    for (u32 e = gtid; e < total; e += gsize)
+    const u32 lane = threadIdx.x & 31u, me = st->rank, P = st->world;
+    const u64 xcap = st->x.xcap;
+    for (u32 e0 = gtid - lane; e0 < total; e0 += gsize) // (warp-uniform trip count: the list positions come from a ballot)
     {
-      {
-        const int32_t d = delta_in[HDR_INTS + e];
-        if (delta_local != delta_in)
-            delta_local[HDR_INTS + e] = 0;
-        if (!d)
-            continue;
-        delta_in[HDR_INTS + e] = 0;
-        const u32 bi = e / (4 * VS), r = e - bi * 4 * VS;
-        const u32 a = st->ba[bi], b = st->bb[bi], z = z0 + bi;
-        const u32 t = r >> 2, vec = r & 3u;
-        u32 ka, kb;
-        if (vec == 0)
+        const u32 e = e0 + lane;
+        const int32_t d = (e < total) ? delta[HDR_INTS + e] : 0;
+        if (d)
+            delta[HDR_INTS + e] = 0;
+        if (xch)
         {
-            ka = t;
-            kb = a;
-        }
-        else if (vec == 1)
-        {
-            ka = b;
-            kb = t;
-        }
-        else if (vec == 2)
-        {
-            ka = t;
-            kb = z;
-        }
-        else
-        {
-            ka = z;
-            kb = t;
-        }
-        const u64 key = (u64)ka | ((u64)kb << 32);
-        const u32 h = murmur3_pair(ka, kb);
-        if (vec >= 2)
-        {
-            const u64 s = table_insert_counted(st, tkey, tmeta, cap, key, h, &s_occ);
-            if (s == NO_SLOT)
+            const u32 mask = __ballot_sync(0xFFFFFFFFu, d != 0);
+            if (mask)
             {
-                atomicOr(&st->err, ERR_TABLE_FULL);
-                continue;
+                const int leader = __ffs(mask) - 1;
+                u32 base = 0;
+                if ((int)lane == leader)
+                    base = atomicAdd(&st->x_count, (u32)__popc(mask));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (d)
+                {
+                    const u64 pos = (u64)base + (u32)__popc(mask & ((1u << lane) - 1u));
+                    if (pos < xcap)
+                    {
+                        const u64 pk = (u64)e | ((u64)(u32)d << 32);
+                        for (u32 p = 0; p < P; p++)
+                            if (p != me)
+                                xchg_entries(st->x.peer[p], xcap, xpar, me)[pos] = pk; // store into the peer's HBM over NVLink
+                    }
+                    else
+                        atomicOr(&st->err, ERR_XCHG_OVERFLOW);
+                }
             }
-            const u32 old = atomicAdd(cnt_ptr(tmeta, s), (u32)d);
-            if (old == 0)
-                atomicAdd(&s_dD, 1);
-            cand_offer(st, s, old + (u32)d);
         }
-        else
+        if (d)
+            apply_entry(st, tkey, tmeta, cap, e, d, VS, z0, &s_dD, &s_occ);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        if (s_dD)
+            atomicAdd(reinterpret_cast<u64 *>(&st->distinct), (u64)(i64)s_dD);
+        if (s_occ)
+            atomicAdd(&st->occupied, (u64)s_occ);
+    }
+}
+
+// The peers' lists for exchange `seq`, as they arrive in my inbox (starting with the right-hand neighbour so that
+// the ranks do not all wait for the same sender first).
+__device__ inline void apply_peer_lists(DevState *st, u32 gtid, u32 gsize, u32 seq)
+{
+    __shared__ int s_dD, s_occ;
+    __shared__ u32 s_cnt;
+    if (threadIdx.x == 0)
+    {
+        s_dD = 0;
+        s_occ = 0;
+    }
+    const u32 nb = st->nb, z0 = st->z;
+    const u32 VS = z0 + nb;
+    u64 *tmeta = st->tmeta, *tkey = st->tkey;
+    const u64 cap = st->tcap, xcap = st->x.xcap;
+    const u32 me = st->rank, P = st->world, par = seq & 1u;
+    for (u32 k = 1; k < P; k++)
+    {
+        const u32 sender = (me + k) % P;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            s_cnt = xchg_wait(st, sender, seq) ? ld_relaxed_sys_u32(st->x.local + XCHG_COUNTS + par * MAX_RANKS + sender) : 0u;
+        __syncthreads();
+        const u32 cnt = s_cnt;
+        const u64 *ent = xchg_entries(st->x.local, xcap, par, sender);
+        for (u32 i = gtid; i < cnt; i += gsize)
         {
-            const u64 s = table_find(tkey, cap, key, h);
-            if (s == NO_SLOT)
-            {
-                atomicOr(&st->err, ERR_MISSING_KEY);
-                continue;
-            }
-            const u32 old = atomicSub(cnt_ptr(tmeta, s), (u32)d);
-            if (old < (u32)d)
-                atomicOr(&st->err, ERR_NEGATIVE);
-            if (old == (u32)d)
-                atomicAdd(&s_dD, -1);
+            const u64 pk = ld_relaxed_sys_u64(ent + i); // written by the peer: not through this SM's L1
+            apply_entry(st, tkey, tmeta, cap, (u32)pk, (int32_t)(u32)(pk >> 32), VS, z0, &s_dD, &s_occ);
         }
-      }
     }
     __syncthreads();
     if (threadIdx.x == 0)
@@ -1592,12 +1780,12 @@ __device__ __forceinline__ void finish_pass(DevState *st)
 }
 
 // whole-table mode: K4 alone (select_kernel follows)
-__global__ void __launch_bounds__(256) apply_kernel(DevState *st, int32_t *delta_in, int32_t *delta_local)
+__global__ void __launch_bounds__(256) apply_kernel(DevState *st, int32_t *delta)
 {
     if (st->stop != STOP_RUN || !st->pending)
         return;
     if (!st->skip)
-        apply_deltas(st, delta_in, delta_local, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+        apply_deltas(st, delta, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, false, 0u);
     __syncthreads();
     if (threadIdx.x == 0)
     {
@@ -1613,31 +1801,81 @@ __global__ void __launch_bounds__(256) apply_kernel(DevState *st, int32_t *delta
 // list mode: K4 + K2 in one launch.  Every block applies its share of the deltas; the last block to
 // finish then owns a consistent table, takes the maximum over the candidate list (one gather per
 // candidate, warp shuffles + block tree with the multiplicity of the maximal key carried along) and
-// decides.  encode: the next rank of the given merge list instead of the maximum.
-__global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st, int32_t *delta_in, int32_t *delta_local, int encode)
+// decides.  mode: AS_TRAIN; AS_ENCODE = the next rank of the given merge list instead of the maximum;
+// AS_APPLY_ONLY = no decision (select_kernel follows: whole-table selection on several GPUs).
+// Several GPUs: the same launch also carries the exchange (struct Xchg): own deltas are pushed into the peers'
+// inboxes while they are applied, the last block to finish raises this rank's flag, and every block then
+// folds in the peers' lists as their flags arrive - no collective, no extra launch.
+enum : int
+{
+    AS_TRAIN = 0,
+    AS_ENCODE = 1,
+    AS_APPLY_ONLY = 2
+};
+__global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st, int32_t *delta, int mode)
 {
     pdl_wait();
     pdl_launch_dependents();
     if (st->stop != STOP_RUN)
         return;
+    const bool encode = (mode == AS_ENCODE);
     __shared__ SelPart sm[SEL_THREADS / 32];
     __shared__ bool s_last;
+    __shared__ u32 s_recs[MAX_RANKS * REC_INTS]; // every rank's edge record (last block and the probe block)
     const u64 t0 = gtime();
     const bool pending = st->pending != 0;
+    const u32 world = st->world;
+    const bool xch = world > 1 && pending && !st->skip; // this launch carries an exchange
+    const u32 seq = st->xseq + (xch ? 1u : 0u);          // the exchange whose records describe the stream from now on
     const u32 nb_apply = gridDim.x - 1; // the last block of the grid only looks up the stream's last pair
     if (blockIdx.x == nb_apply)
     {
-        if (threadIdx.x == 0 && !encode)
+        if (xch && threadIdx.x < 32)
         {
-            const bool flip0 = pending && !st->skip;
-            const u64 key = last_pair_key(st, reinterpret_cast<const u32 *>(delta_in), flip0 ? (st->cur ^ 1u) : st->cur,
-                                          flip0 ? st->layout_next : st->layout, flip0 ? st->n_next : st->n);
-            st->probe_key = key;
-            st->probe_slot = (key == EMPTY_KEY) ? NO_SLOT : table_find(st->tkey, st->tcap, key, murmur3_pair((u32)key, (u32)(key >> 32)));
+            u32 rec[REC_INTS];
+            edge_record_compute(st, true, rec);
+            if (threadIdx.x == 0)
+                xchg_push_record(st, seq, rec);
         }
     }
     else if (pending && !st->skip)
-        apply_deltas(st, delta_in, delta_local, blockIdx.x * blockDim.x + threadIdx.x, nb_apply * blockDim.x);
+        apply_deltas(st, delta, blockIdx.x * blockDim.x + threadIdx.x, nb_apply * blockDim.x, xch, seq & 1u);
+    if (xch)
+    {
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            __threadfence_system();
+            if (atomicAdd(&st->x_done, 1u) == gridDim.x - 1)
+            {
+                // every block of this rank has pushed its entries: my list is complete
+                st->x_done = 0;
+                const u32 cnt = atomicExch(&st->x_count, 0u);
+                xchg_signal(st, seq, cnt < st->x.xcap ? cnt : (u32)st->x.xcap);
+            }
+        }
+        if (blockIdx.x != nb_apply)
+            apply_peer_lists(st, blockIdx.x * blockDim.x + threadIdx.x, nb_apply * blockDim.x, seq);
+        else if (threadIdx.x == 0)
+        {
+            bool ok = true;
+            for (u32 p = 0; p < world && ok; p++)
+                if (p != st->rank)
+                    ok = xchg_wait(st, p, seq);
+        }
+        __syncthreads();
+    }
+    if (world > 1 && (blockIdx.x == nb_apply) && threadIdx.x < MAX_RANKS * REC_INTS)
+        s_recs[threadIdx.x] = ld_relaxed_sys_u32(xchg_recs(st->x.local, seq & 1u) + threadIdx.x);
+    __syncthreads();
+    if (blockIdx.x == nb_apply && threadIdx.x == 0 && mode == AS_TRAIN)
+    {
+        const bool flip0 = pending && !st->skip;
+        const u64 key = last_pair_key(st, s_recs, flip0 ? (st->cur ^ 1u) : st->cur, flip0 ? st->layout_next : st->layout,
+                                      flip0 ? st->n_next : st->n);
+        st->probe_key = key;
+        st->probe_slot = (key == EMPTY_KEY) ? NO_SLOT : table_find(st->tkey, st->tcap, key, murmur3_pair((u32)key, (u32)(key >> 32)));
+    }
     __syncthreads();
     const u64 t1 = gtime();
     if (threadIdx.x == 0)
@@ -1653,23 +1891,23 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
     // ---- last block: the table is final.  Side jobs (flip the buffers, census probe, threshold test)
     // run on three different warps while everybody scans the candidates.
     __shared__ PreDecide s_pre;
-    const bool flip = pending && !st->skip;
-    const u32 cur0 = st->cur;
-    const u32 nbuf = flip ? (cur0 ^ 1u) : cur0;
-    const u32 nlayout = flip ? st->layout_next : st->layout;
-    const u64 nn = flip ? *reinterpret_cast<volatile u64 *>(&st->n_next) : st->n;
+    if (world > 1 && threadIdx.x < MAX_RANKS * REC_INTS)
+        s_recs[threadIdx.x] = ld_relaxed_sys_u32(xchg_recs(st->x.local, seq & 1u) + threadIdx.x);
     const u64 D = (u64) * reinterpret_cast<volatile i64 *>(&st->distinct);
     __syncthreads();
     if (threadIdx.x == 0)
     {
         st->sel_done = 0;
+        st->xseq = seq;
         if (pending)
             finish_pass(st);
     }
+    if (mode == AS_APPLY_ONLY)
+        return;
     if (encode)
     {
         if (threadIdx.x == 0)
-            decide_rank(st, delta_in);
+            decide_rank(st, s_recs);
         return;
     }
     if (threadIdx.x == 32)
@@ -1754,7 +1992,7 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
         }
         else
         {
-            decide(st, k, s, m, delta_in, &s_pre); // several GPUs: the general form
+            decide(st, k, s, m, s_recs, &s_pre); // several GPUs: the general form
             extend = fits && st->stop == STOP_RUN && st->pending && st->batch_max > 1 && st->cand_T && st->want_ranged &&
                      !st->static_mode && !tok_alias(st->a, st->b) && st->z >= st->batch_min_z && st->z >= st->hist_max &&
                      st->merges_done < st->max_merges;
@@ -1793,8 +2031,14 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
         //     exceed the old pairs they come from);
         //   * D stays far enough from every table-doubling threshold that the bucket order B(D) and the
         //     workers' bucket counts cannot change inside the batch.
-        constexpr int NW = SEL_THREADS / 32, TOPK = 4;
-        __shared__ u64 s_wk[NW][TOPK], s_wp[NW][TOPK];
+        // Several GPUs: every rank must form the SAME batch, but the candidate list is in a different order on every
+        // rank (it is filled by atomics), so which warp holds which candidate differs.  With as many entries per warp
+        // list as a batch has merges no list can be used up before the cap ends the walk, and the walk depends on
+        // the SET of candidates only.  (One GPU: four per warp are cheaper to extract, and any prefix of the
+        // sequential merges is a correct batch.)
+        constexpr int NW = SEL_THREADS / 32, TOPK_MAX = BATCH_MAX > 4 ? BATCH_MAX : 4;
+        const int TOPK = (world > 1) ? TOPK_MAX : 4;
+        __shared__ u64 s_wk[NW][TOPK_MAX], s_wp[NW][TOPK_MAX];
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const u64 first = s_win;
 #pragma unroll
@@ -1964,7 +2208,7 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
             for (int j = 0; j < UNR; j++)
                 if (kk[j])
                     look(kk[j], pk[j]);
-            if (threadIdx.x < NW * TOPK)
+            if ((int)threadIdx.x < NW * TOPK)
                 look(s_wk[threadIdx.x / TOPK][threadIdx.x % TOPK], s_wp[threadIdx.x / TOPK][threadIdx.x % TOPK]);
 #pragma unroll
             for (int o = 16; o; o >>= 1)
@@ -2108,10 +2352,10 @@ __global__ void __launch_bounds__(256) cand_rebuild_kernel(DevState *st, u32 T)
 __global__ void cand_big_ok_kernel(DevState *st) { st->cand_big_ok = 1; }
 
 // halos of the untouched stream (before the first merge), for the shard-straddling byte pair
-__global__ void resolve_edges_kernel(DevState *st, const int32_t *delta_reduced)
+__global__ void resolve_edges_kernel(DevState *st)
 {
     if (st->world > 1)
-        resolve_edges(st, reinterpret_cast<const u32 *>(delta_reduced), SENT, false);
+        resolve_edges(st, cur_recs(st), SENT, false);
     else
         st->n_global = st->n;
 }

@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(256) entry_pass2_kernel(DevState *st, ResState
     }
 }
 
-__global__ void resolver_commit_kernel(DevState *st, ResState *rs, const int32_t *delta_reduced)
+__global__ void resolver_commit_kernel(DevState *st, ResState *rs)
 {
     if (st->stop != STOP_PAUSE)
         return;
@@ -478,7 +478,7 @@ __global__ void resolver_commit_kernel(DevState *st, ResState *rs, const int32_t
         }
     }
     const u64 key = st->tkey[best_slot];
-    commit_merge(st, (u32)(key & 0xFFFFFFFFull), (u32)(key >> 32), rs->fmax, reinterpret_cast<const u32 *>(delta_reduced));
+    commit_merge(st, (u32)(key & 0xFFFFFFFFull), (u32)(key >> 32), rs->fmax, cur_recs(st));
     st->stop = STOP_RUN;
     st->pause = 0;
 }

@@ -307,6 +307,23 @@ def test_sharded_training_and_encoding_match_oracle(engine, oracle, P):
     assert_encode_case(engine, oracle, "enc_zipfa3m_300", m, n_gpus=P)
 
 
+@pytest.mark.parametrize("P", [2, 8])
+def test_exchange_inbox_growth(engine, oracle, P, monkeypatch):
+    """The peers' inboxes start at 64 entries per slot here (default 262,144): they must be re-allocated and their
+    handles re-exchanged in mid-run, several times, without anybody noticing."""
+    if _device_count() < P:
+        pytest.skip(f"needs {P} GPUs")
+    monkeypatch.setenv("BPE_CUDA_XCHG_CAP", "64")
+    assert_case(engine, oracle, "zipfa8m_200", n_gpus=P)
+    assert_case(engine, oracle, "zipfa12m_1300", n_gpus=P)
+
+
+def test_more_gpus_than_devices_is_an_error(engine):
+    with pytest.raises(engine.BpeCudaError) as e:
+        engine.train(np.frombuffer(b"abababab" * 100, dtype=np.uint8), n_gpus=_device_count() + 1)
+    assert e.value.rc in (-4, -1)
+
+
 def test_config2_full_size_matches_the_oracle_digest(engine):
     """BASELINE config 2 at its full size (100 MB, 4,096 merges): the oracle needs four minutes for it, so its
     result is committed as two SHA-256 digests (tests/golden/c2_full.json, tools/make_c2_golden.py)."""
