@@ -62,6 +62,9 @@ struct NcclApi
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
@@ -86,7 +89,11 @@ static int nccl_load()
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
     g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.AllGather || !g_nccl.CommDestroy)
+    g_nccl.Broadcast = (decltype(g_nccl.Broadcast))dlsym(h, "ncclBroadcast");
+    g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(h, "ncclGroupEnd");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.AllGather || !g_nccl.CommDestroy ||
+        !g_nccl.Broadcast || !g_nccl.GroupStart || !g_nccl.GroupEnd)
     {
         set_error("NCCL library lacks required symbols");
         return BPE_CUDA_ERR_CUDA;
@@ -196,6 +203,11 @@ struct bpe_cuda_ctx
     // communicator (bootstrap + the two collectives of a run's start) and the peer-memory exchange (struct Xchg)
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
+    bool solo = false;                // this run has been CONSOLIDATED: the global stream fell below 1,048,576 tokens, every
+                                      // rank now holds all of it and runs the single-GPU algorithm (exact 16-slice census
+                                      // and chain-order resolver); no exchange any more
+    u32 *d_gather = nullptr;          // the whole stream on this rank, for the exact tie-break above the static limit
+    size_t gather_cap = 0;
     Xchg hx{};                        // host copy of the exchange descriptor (goes into DevState at the start of a run)
     u32 xseq = 0;                     // exchanges completed so far (continues from run to run: the flags are never reset)
     size_t xcap_opt = 0;              // test knob: initial entries per inbox slot
@@ -225,6 +237,8 @@ struct bpe_cuda_ctx
 };
 
 static inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+// the stream of this run is cut into shards that exchange deltas and edge records
+static inline bool sharded(const bpe_cuda_ctx *c) { return c->world > 1 && !c->solo; }
 // Merges that may share one pass (the exchange between GPUs carries the touched counters only, so its cost does not
 // depend on the batch size or the vocabulary: the same limit for every world size).
 static inline size_t eff_batch(const bpe_cuda_ctx *c)
@@ -400,7 +414,7 @@ static int xchg_setup(bpe_cuda_ctx *c, size_t xcap)
 // merge, 0 = unknown) bounds every later merge's replacements.  Every rank calls this with the same arguments.
 static int ensure_xchg(bpe_cuda_ctx *c, size_t z_ub, u64 freq_bound)
 {
-    if (c->world <= 1)
+    if (!sharded(c))
         return 0;
     const size_t bm = eff_batch(c);
     size_t need = bm * 4 * (z_ub + bm + 1);
@@ -835,7 +849,7 @@ static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool c
     }
     else
     {
-        if (c->world > 1)
+        if (sharded(c))
             CU(launch_chained(c, apply_select_kernel, agrid + 1, SEL_THREADS, 0, c->d_st, c->d_delta, (int)AS_APPLY_ONLY));
         else
         {
@@ -917,6 +931,7 @@ static int poll_wait(bpe_cuda_ctx *c, int slot)
 
 // Same-bucket ties / exact-threshold iterations / layout changes / candidate rebuilds.
 static int resolve_pause(bpe_cuda_ctx *c, bool encode);
+static int consolidate(bpe_cuda_ctx *c);
 
 static int run_loop(bpe_cuda_ctx *c, bool encode)
 {
@@ -1022,8 +1037,8 @@ static int run_loop(bpe_cuda_ctx *c, bool encode)
         // Worker-table growth is only possible while some slice can still hold thr(B_t) distinct pairs.
         // (every rank must take the same decisions about what it enqueues - the collectives have to
         // match - so anything that steers the batch structure looks at replicated state only)
-        const bool stat = (c->world > 1 ? h->n_global : h->n) < STATIC_LIMIT;
-        if (!encode && c->world == 1)
+        const bool stat = (sharded(c) ? h->n_global : h->n) < STATIC_LIMIT;
+        if (!encode && !sharded(c))
         {
             if (c->force_census)
                 X.census = true;
@@ -1184,6 +1199,7 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
     CU(cudaSetDevice(c->device));
     const auto t0 = std::chrono::steady_clock::now();
     c->run_encode = encode;
+    c->solo = false;
     c->run_max_merges = encode ? 0 : max_merges;
     memset(&c->stats, 0, sizeof c->stats);
     for (double &x : c->host_ms)
@@ -1312,6 +1328,14 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
             const u32 one = 1;
             CU(cudaMemcpyAsync(&c->d_st->static_mode, &one, sizeof one, cudaMemcpyHostToDevice, c->stream));
             c->h_st->static_mode = 1;
+            if (c->world > 1)
+            {
+                // a corpus that small is not worth sharding, and the static slices need the whole stream anyway
+                if ((rc = consolidate(c)))
+                    return rc;
+                if ((rc = poll_state(c)))
+                    return rc;
+            }
         }
     }
 
@@ -1341,9 +1365,11 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
                 (unsigned long long)h->ext_why[0], (unsigned long long)h->ext_why[1], (unsigned long long)h->ext_why[2],
                 (unsigned long long)h->ext_why[3], (unsigned long long)h->ext_why[4], (unsigned long long)h->ext_why[5], (unsigned long long)h->ext_why[6], (unsigned long long)h->ext_why[7]);
     c->res_n_merges = (size_t)h->merges_done;
-    c->res_n_tokens = (size_t)h->n;
+    // (consolidated run: every rank holds the whole stream; rank 0 reports it, so that the ranks' results still
+    // concatenate to the stream)
+    c->res_n_tokens = (c->solo && c->rank != 0) ? 0 : (size_t)h->n;
     c->stats.n_merges = h->merges_done;
-    c->stats.n_tokens = (c->world > 1) ? h->n_global : h->n;
+    c->stats.n_tokens = sharded(c) ? h->n_global : h->n;
     c->stats.ranks_applied = h->ranks_applied;
     c->stats.same_bucket_ties = h->same_bucket_ties;
     c->stats.threshold_edges = h->threshold_edges;
@@ -1396,34 +1422,135 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
 }
 
 // ---------------------------------------------------------------------------------------------
-// pause handling
-__global__ void tie_reset_kernel(DevState *st) { st->probe_key = ~0ull; }
-__global__ void tie_min_key_kernel(DevState *st)
+// Exactness on several GPUs (hash_table.c:208-223,248-254,300-338; bpe.c:449-477).  The chain order inside one
+// bucket and the 16 worker tables' bucket counts depend on WHERE in the stream a pair is first seen, i.e. on
+// positions in the whole stream.  Two rare situations need them, and both are handled by giving every rank the whole
+// stream and letting it run the single-GPU kernels (all ranks compute the same thing, nothing has to be agreed on):
+//   * the global stream falls below 1,048,576 tokens (the reference's static slicing, at most 4 MB): the run is
+//     CONSOLIDATED for good - sharding a stream that fits in L2 many times over buys nothing;
+//   * a same-bucket tie / an exact-threshold iteration above that limit: the stream is gathered into a scratch
+//     buffer for the resolver kernels only, and the shards carry on afterwards.
+// The gathers are NCCL broadcasts (rare, off the per-pass path).
+static int read_shard_lengths(bpe_cuda_ctx *c, std::vector<u64> &lens, u64 *total)
 {
-    if (st->stop != STOP_PAUSE)
-        return;
-    const u64 cap = st->tcap;
-    const u64 B = merged_buckets((u64)st->distinct);
-    const u32 bmask = (u32)(B - 1);
-    const u64 want = st->sel_key;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x)
+    std::vector<u32> hdr(HDR_INTS);
+    CU(cudaMemcpyAsync(hdr.data(), c->hx.local + XCHG_RECS + (c->h_st->xseq & 1u) * MAX_RANKS * REC_INTS, HDR_INTS * sizeof(u32),
+                       cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    lens.assign((size_t)c->world, 0);
+    *total = 0;
+    for (int r = 0; r < c->world; r++)
     {
-        const u64 mv = st->tmeta[i];
-        if ((mv >> 32) && ((mv & 0xFFFFFFFF00000000ull) | (u64)(0xFFFFFFFFu - ((u32)mv & bmask))) == want)
-            atomicMin(&st->probe_key, st->tkey[i]);
+        lens[(size_t)r] = (u64)hdr[r * REC_INTS] | ((u64)hdr[r * REC_INTS + 1] << 32);
+        *total += lens[(size_t)r];
     }
-}
-__global__ void tier_a_commit_kernel(DevState *st)
-{
-    // sharded stream: among the pairs that tie inside the winning bucket, the smallest pair key (same on every rank)
-    if (st->stop != STOP_PAUSE)
-        return;
-    const u64 key = st->probe_key != ~0ull ? st->probe_key : st->tkey[st->sel_slot];
-    commit_merge(st, (u32)(key & 0xFFFFFFFFull), (u32)(key >> 32), (u32)(st->sel_key >> 32), cur_recs(st));
-    st->stop = STOP_RUN;
-    st->pause = 0;
+    return 0;
 }
 
+// dst[0 .. n_global) = the ranks' dense streams in rank order, on every rank (c->h_st must be current and DENSE)
+static int gather_stream(bpe_cuda_ctx *c, u32 *dst, const std::vector<u64> &lens)
+{
+    const u32 *mine = c->h_st->tok[c->h_st->cur];
+    NC(g_nccl.GroupStart());
+    u64 off = 0;
+    for (int r = 0; r < c->world; r++)
+    {
+        if (lens[(size_t)r])
+            NC(g_nccl.Broadcast(r == c->rank ? (const void *)mine : (const void *)(dst + off), dst + off, (size_t)lens[(size_t)r], ncclUint32,
+                                r, c->comm, c->stream));
+        off += lens[(size_t)r];
+    }
+    NC(g_nccl.GroupEnd());
+    return 0;
+}
+
+__global__ void consolidate_kernel(DevState *st, u32 *t0, u32 *t1, u64 n)
+{
+    st->tok[0] = st->tok_real[0] = t0;
+    st->tok[1] = st->tok_real[1] = t1;
+    st->cur = 0;
+    st->n = st->n_global = n;
+    st->layout = st->layout_next = LAYOUT_DENSE;
+    st->world = 1;
+    st->rank = 0;
+    st->halo_before[0] = st->halo_before[1] = SENT;
+    st->halo_after[0] = st->halo_after[1] = st->halo_after[2] = SENT;
+    st->carry_in = 0;
+    st->static_mode = 1;
+}
+
+// the resolver kernels read the stream through tok[cur] / n: point them at the gathered copy, and back
+__global__ void stream_view_kernel(DevState *st, u32 *view, u64 n)
+{
+    if (view)
+    {
+        st->probe_slot = (u64)st->tok[st->cur]; // (scratch fields: nothing else uses them during a pause)
+        st->probe_key = st->n;
+        st->tok[st->cur] = view;
+        st->n = n;
+    }
+    else
+    {
+        st->tok[st->cur] = reinterpret_cast<u32 *>(st->probe_slot);
+        st->n = st->probe_key;
+    }
+}
+
+static int consolidate(bpe_cuda_ctx *c)
+{
+    int rc;
+    if ((rc = poll_state(c)))
+        return rc;
+    if (c->h_st->layout != LAYOUT_DENSE)
+    {
+        set_error("consolidate: the stream is not dense");
+        return BPE_CUDA_ERR_STATE;
+    }
+    std::vector<u64> lens;
+    u64 total = 0;
+    if ((rc = read_shard_lengths(c, lens, &total)))
+        return rc;
+    const size_t cap = round_up((size_t)total, V_TILE) + V_TILE + 64;
+    u32 *nt[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; i++)
+    {
+        CU(cudaMalloc(&nt[i], cap * sizeof(u32)));
+        CU(cudaMemsetAsync(nt[i], 0xFF, 16, c->stream)); // the 4 readable slots in front
+    }
+    if ((rc = gather_stream(c, nt[0] + 4, lens)))
+        return rc;
+    consolidate_kernel<<<1, 1, 0, c->stream>>>(c->d_st, nt[0] + 4, nt[1] + 4, total);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 2; i++)
+    {
+        CU(cudaFree(c->d_tok_alloc[i]));
+        c->d_tok_alloc[i] = nt[i];
+    }
+    c->tok_cap = cap;
+    const size_t tiles = (size_t)total / R_TILE + 2;
+    if (tiles > c->desc_cap)
+    {
+        CU(cudaFree(c->d_desc));
+        CU(cudaFree(c->d_pdesc));
+        c->d_desc = nullptr;
+        c->d_pdesc = nullptr;
+        CU(cudaMalloc(&c->d_desc, tiles * sizeof(u64)));
+        CU(cudaMalloc(&c->d_pdesc, tiles * sizeof(u32)));
+        c->desc_cap = tiles;
+    }
+    CU(cudaMemsetAsync(c->d_desc, 0, c->desc_cap * sizeof(u64), c->stream));
+    CU(cudaMemsetAsync(c->d_pdesc, 0, c->desc_cap * sizeof(u32), c->stream));
+    c->solo = true;
+    c->want_ranged = 0;
+    if (c->debug)
+        fprintf(stderr, "[bpe_cuda r%d] consolidated: %llu tokens on every rank from here on\n", c->rank, (unsigned long long)total);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pause handling
 static int resolve_pause(bpe_cuda_ctx *c, bool encode)
 {
     HostTimer ht(&c->host_ms[2]);
@@ -1471,7 +1598,10 @@ static int resolve_pause(bpe_cuda_ctx *c, bool encode)
     }
     if (pause & PAUSE_STATIC)
     {
-        // the select kernel latched static_mode; nothing else to do but resume (and select again)
+        // the select kernel latched static_mode; several GPUs: from here on every rank works on the whole stream;
+        // then resume (and select again)
+        if (sharded(c) && !encode && (rc = consolidate(c)))
+            return rc;
         resume_kernel<<<1, 1, 0, c->stream>>>(c->d_st);
         c->launches++;
         return 0;
@@ -1483,23 +1613,41 @@ static int resolve_pause(bpe_cuda_ctx *c, bool encode)
         return rc;
     if ((rc = ensure_logs(c, (size_t)(merges_done + 2))))
         return rc;
-    if (c->world > 1)
+    u64 n_res = n; // tokens the resolver kernels look at
+    if (sharded(c))
     {
-        // sharded stream: chain order is taken from the table order (documented limitation; counted)
-        // (the smallest pair key among the tied pairs: slot numbers differ from rank to rank, pair keys do not)
-        tie_reset_kernel<<<1, 1, 0, c->stream>>>(c->d_st);
-        tie_min_key_kernel<<<(int)std::min<u64>((c->tcap + 255) / 256, (u64)c->sm_count * 8), 256, 0, c->stream>>>(c->d_st);
-        tier_a_commit_kernel<<<1, 1, 0, c->stream>>>(c->d_st);
-        c->launches += 3;
-        return enqueue_step(c, (u32)(256 + merges_done), n, encode, false, false);
+        // chain order needs positions in the WHOLE stream: gather it on every rank (scratch) for the resolver kernels
+        if ((rc = poll_state(c))) // (the repack above moved the stream)
+            return rc;
+        std::vector<u64> lens;
+        if ((rc = read_shard_lengths(c, lens, &n_res)))
+            return rc;
+        if (n_res >= 0xFFFFFFF0ull)
+        {
+            set_error("a same-bucket tie on a sharded stream of %llu tokens: first-sight positions are kept in 32 bits",
+                      (unsigned long long)n_res);
+            return BPE_CUDA_ERR_STATE;
+        }
+        if (n_res + 16 > c->gather_cap)
+        {
+            CU(cudaFree(c->d_gather));
+            c->d_gather = nullptr;
+            c->gather_cap = 0;
+            CU(cudaMalloc(&c->d_gather, (n_res + 16) * sizeof(u32)));
+            c->gather_cap = n_res + 16;
+        }
+        if ((rc = gather_stream(c, c->d_gather, lens)))
+            return rc;
+        stream_view_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_gather, n_res);
+        c->launches++;
     }
-    const u32 slices = (n < STATIC_LIMIT) ? REF_THREADS : 1;
-    if ((rc = ensure_resolver(c, n, slices)))
+    const u32 slices = (n_res < STATIC_LIMIT) ? REF_THREADS : 1;
+    if ((rc = ensure_resolver(c, n_res, slices)))
         return rc;
-    if ((rc = enqueue_census(c, n, 1)))
+    if ((rc = enqueue_census(c, n_res, 1)))
         return rc;
-    const int g = pos_grid(c, n);
-    const int tg = (int)std::max<u64>(1, std::min<u64>(n / SCAN_TILE + 1, (u64)c->sm_count * 8));
+    const int g = pos_grid(c, n_res);
+    const int tg = (int)std::max<u64>(1, std::min<u64>(n_res / SCAN_TILE + 1, (u64)c->sm_count * 8));
     const int sg = (int)std::min<u64>((c->tcap + 255) / 256, (u64)c->sm_count * 8);
     rank_tile_count_kernel<<<tg, 256, 0, c->stream>>>(c->d_rs, c->d_first, c->d_pos_slot, c->d_tile_cnt);
     rank_tile_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_rs, c->d_tile_cnt, c->d_tile_off);
@@ -1509,6 +1657,11 @@ static int resolve_pause(bpe_cuda_ctx *c, bool encode)
     cand_bucket_kernel<<<sg, 256, 0, c->stream>>>(c->d_st, c->d_rs);
     cand_collect_kernel<<<sg, 256, 0, c->stream>>>(c->d_st, c->d_rs, c->d_first, c->d_rank);
     entry_pass2_kernel<<<g, 256, 0, c->stream>>>(c->d_st, c->d_rs, c->d_first, c->d_pos_slot, c->d_rank);
+    if (sharded(c))
+    {
+        stream_view_kernel<<<1, 1, 0, c->stream>>>(c->d_st, nullptr, 0); // back to this rank's shard
+        c->launches++;
+    }
     resolver_commit_kernel<<<1, 1, 0, c->stream>>>(c->d_st, c->d_rs);
     c->launches += 9;
     CU(cudaGetLastError());
@@ -1650,6 +1803,7 @@ void bpe_cuda_ctx_destroy(bpe_cuda_ctx_t *c)
     }
     cudaFree(c->d_delta);
     cudaFree(c->d_hello);
+    cudaFree(c->d_gather);
     for (void *p : c->x_mapped)
         cudaIpcCloseMemHandle(p);
     for (void *p : c->x_owned)

@@ -49,12 +49,12 @@ def _runs(P):
     return np.repeat(rng.integers(97, 100, 400_000, dtype=np.uint8), rng.integers(1, 30, 400_000))[:4_000_001]
 
 
-def _tie_heavy():
+def _tie_heavy(copies=60):
     # the 20 KB random-text prefix (9 same-bucket ties when trained alone) repeated past 1,048,576 tokens with a
     # different separator byte between the copies: trained to exhaustion the late merges tie all the time
     rt = _random_text()[:20000]
     parts = []
-    for k in range(60):
+    for k in range(copies):
         parts.append(rt[(k * 37) % 500:])
         parts.append(np.array([1 + k % 31], dtype=np.uint8))
     return np.concatenate(parts)
@@ -81,6 +81,8 @@ TRAIN_CASES = {
     "cross1m_400": (lambda: corpus(0, 1_400_000, 21), 400),
     # tie-heavy, to exhaustion, above and below the static limit
     "ties1m2_exh": (_tie_heavy, 0),
+    # 4.3 M tokens that stay above the static limit for all 1,000 merges, 4 of them same-bucket ties
+    "ties4m_1000": (lambda: _tie_heavy(220), 1000),
 }
 for _r in (1, 5, 64, 0):
     for _i in range(3):
