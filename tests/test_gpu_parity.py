@@ -354,6 +354,30 @@ def test_more_gpus_than_devices_is_an_error(engine):
     assert e.value.rc in (-4, -1)
 
 
+def _full_golden(name):
+    import json
+    import os
+    here = os.path.dirname(__file__)
+    g = json.load(open(os.path.join(here, "golden", name + ".json")))
+    g["merge_list"] = np.load(os.path.join(here, "golden", "full", name + "_merges.npz"))["merges"]
+    return g
+
+
+def test_config1_random_text_to_exhaustion_matches_the_oracle(engine):
+    """BASELINE config 1: the reference's bundled random_text.txt (1,048,576 bytes) with its default merge count,
+    i.e. to exhaustion (bpe.c:745): 39,716 merges, 154 of them same-bucket ties, iteration 0 in the dynamic regime
+    (n = 2^20 is not below the limit, bpe.c:449), all others in the static one.  The oracle needs 11 minutes; its merge
+    list and the digest of its ids are committed (tools/make_full_golden.py c1_exhaustion)."""
+    g = _full_golden("c1_exhaustion")
+    data = oracle_api.golden("rt_full_cap300")["input"]
+    assert data.size == g["corpus"]["bytes"]
+    m, t, st = engine.train(data)
+    exp = {"merges": g["merge_list"], "n_ids": g["n_ids"], "ids_sha256": g["ids_sha256"], "same_bucket_ties": g["same_bucket_ties"],
+           "threshold_edges": g["threshold_edges"], "thread_buckets": g["thread_buckets"]}
+    check_result(exp, m, t, st, 1, "config 1 to exhaustion")
+    assert len(m) == 39716 and st["final_distinct"] == g["final_distinct"]
+
+
 def test_config2_full_size_matches_the_oracle_digest(engine):
     """BASELINE config 2 at its full size (100 MB, 4,096 merges): the oracle needs four minutes for it, so its
     result is committed as two SHA-256 digests (tests/golden/c2_full.json, tools/make_c2_golden.py)."""
