@@ -636,7 +636,12 @@ def main():
         # The 1/2/4/8 curve is asked for on the 1 GB corpus (BASELINE.json configs[2]); it fits one GPU, so every N runs
         # it and the per-N values are comparable.  Config 2 (100 MB, 1 GPU) is measured inside the N = 1 line ("c2").
         args.workload = os.environ.get("BPE_BENCH_WORKLOAD") or "c3"
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    if os.environ.get("BPE_BENCH_SCALE"):
+        # plumbing test only (tests / dry runs): a smaller corpus of the same kind; the line says so in config.workload
+        f = float(os.environ["BPE_BENCH_SCALE"])
+        w["size"] = int(w["size"] * f)
+        w["desc"] += f" [SCALED x{f}: NOT the named configuration]"
     rank, world, local = dist_setup(args.gpus)
     if args.impl == "reference":
         bench_reference(args, w, rank, world)

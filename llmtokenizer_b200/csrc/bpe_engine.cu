@@ -212,6 +212,7 @@ struct bpe_cuda_ctx
     u32 xseq = 0;                     // exchanges completed so far (continues from run to run: the flags are never reset)
     size_t xcap_opt = 0;              // test knob: initial entries per inbox slot
     u64 x_timeout_ms = 20000;         // BPE_CUDA_XCHG_TIMEOUT_MS
+    int agrid_max = 120;              // blocks of apply_select_kernel that fold deltas into the table (BPE_CUDA_AGRID_MAX)
     void *d_hello = nullptr;          // staging of the handle exchange
     std::vector<void *> x_owned;      // every inbox this context ever allocated (freed with the context: a peer may still
                                       // have an old one mapped)
@@ -840,7 +841,9 @@ static int enqueue_step(bpe_cuda_ctx *c, u32 z, u64 n_upper, bool encode, bool c
     // every thread looks at one token's four counters (128 bits) per trip; 32 blocks keep the "last block" wait short
     // (batches are mostly short: size the grid for two merges, the loop is grid-stride).  Several GPUs: the same
     // launch pushes this rank's touched counters into the peers' inboxes and folds theirs in (struct Xchg).
-    const int agrid = (int)std::min<u64>((std::min<u64>(eff_batch(c), 2) * 4ull * (z + 1) + SEL_THREADS - 1) / SEL_THREADS, 64);
+    // (a thread takes one token's four counters per trip: aim at two trips for a pass of four merges; at least 64
+    // blocks - few chains per thread - and at most 120, so that the whole grid is resident next to the pass kernel)
+    const int agrid = (int)std::max<u64>(64, std::min<u64>((std::min<u64>(eff_batch(c), 4) * (u64)(z + 1)) / (2 * SEL_THREADS), (u64)c->agrid_max));
     if (encode || c->cand_T)
     {
         CU(launch_chained(c, apply_select_kernel, agrid + 1, SEL_THREADS, 0, c->d_st, c->d_delta, encode ? (int)AS_ENCODE : (int)AS_TRAIN));
@@ -1765,6 +1768,8 @@ int bpe_cuda_ctx_create(int device, bpe_cuda_ctx_t **out)
         c->pdl = atoi(e) != 0;
     if (const char *e = getenv("BPE_CUDA_SPECULATE"))
         c->speculate = atoi(e) != 0;
+    if (const char *e = getenv("BPE_CUDA_AGRID_MAX"))
+        c->agrid_max = std::max(64, atoi(e));
     if (const char *e = getenv("BPE_CUDA_XCHG_TIMEOUT_MS"))
         c->x_timeout_ms = (u64)std::max(1, atoi(e));
     if (const char *e = getenv("BPE_CUDA_XCHG_CAP"))

@@ -50,7 +50,7 @@ enum : u32
     PAUSE_TIE = 1,    // >= 2 maximal pairs share the winning bucket: chain order decides
     PAUSE_EDGE = 2,   // D sits exactly on a doubling threshold of the merged table
     PAUSE_STATIC = 4, // stream fell below 1,048,576 tokens: reference switches to static slicing
-    PAUSE_SAME = 8,   // a == b was selected (and committed) while the stream is RANGED: needs the general kernel
+    PAUSE_SAME = 8,   // (unused since a == b passes run inside replace_stream_kernel; kept for the host's pause handler)
     PAUSE_REBUILD = 16 // the best candidate fell below the list's threshold: the list must be rebuilt
 };
 enum : u32
@@ -126,6 +126,7 @@ struct DevState
     u32 *rcnt[2];
     u32 *redge[2];
     u32 rp_done, inplace; // inplace: a RANGED stream is compacted inside its own buffer (tok[0] == tok[1])
+    u32 rpar[RANGE_MAX];  // a == b passes: per range, epoch << 2 | whole range is one run << 1 | parity of its trailing run
     u32 *tok_real[2];     // the two allocations; tok[] aliases one of them while RANGED and in place
     u64 ext_why[8];       // debug statistics: why batch extensions ended (see apply_select_kernel)
     // delta entries that became non-zero in the current pass (single GPU): apply walks this list instead of
@@ -983,12 +984,6 @@ __device__ inline void decide_list(DevState *st, u64 k, u64 s, u32 m, const PreD
     st->merges_done = md + 1;
     st->epoch = epoch + 1;
     st->ticket = 0;
-    if (a == b && wr && !stat)
-    {
-        st->pause = PAUSE_SAME; // see decide()
-        st->stop = STOP_PAUSE;
-        return;
-    }
     out->ok = (batch_max > 1 && cand_T && wr && !stat && !tok_alias(a, b) && z >= batch_min_z && z >= hist_max && md + 1 < mm) ? 1u : 0u;
     out->a = a;
     out->b = b;
@@ -1057,12 +1052,7 @@ __device__ inline void decide(DevState *st, u64 k, u64 s, u32 m, const u32 *rec_
     }
     const u64 key = st->tkey[s];
     commit_merge(st, (u32)(key & 0xFFFFFFFFull), (u32)(key >> 32), freq, rec_all, false, pre);
-    if (st->a == st->b && st->want_ranged && !st->static_mode)
-    {
-        // run-parity pairing needs the general kernel on a dense stream: the host repacks, then resumes
-        st->pause = PAUSE_SAME;
-        st->stop = STOP_PAUSE;
-    }
+    // (a == b on a RANGED stream: replace_stream_kernel takes its run-parity path, same_pair_range)
 }
 
 // encode: the "selection" is simply the next rank of the given merge list; a rank whose pair does
@@ -1084,12 +1074,7 @@ __device__ inline void decide_rank(DevState *st, const u32 *rec_all)
     else
     {
         st->ranks_applied++;
-        if (a == b && st->want_ranged && !st->static_mode)
-        {
-            st->pause = PAUSE_SAME;
-            st->stop = STOP_PAUSE;
-        }
-        else if (!tok_alias(a, b) && st->batch_max > 1 && st->want_ranged && !st->static_mode && st->z >= st->batch_min_z &&
+        if (!tok_alias(a, b) && st->batch_max > 1 && st->want_ranged && !st->static_mode && st->z >= st->batch_min_z &&
                  st->z >= st->hist_max)
         {
             // The following ranks can share this pass as long as nothing connects them: pairwise different tokens,
@@ -1585,73 +1570,115 @@ __device__ __forceinline__ u64 table_insert_counted(DevState *st, u64 *tkey, u64
     return NO_SLOT;
 }
 
-// one delta counter -> the pair table.  Entry e of the delta vectors: merge i of the batch owns the block
+// One delta counter -> the pair table.  Entry e of the delta vectors: merge i of the batch owns the block
 // [i * 4 * VS, (i + 1) * 4 * VS), VS = z + nb (one slot per token id that exists after the pass); inside a block,
-// token t holds {-(t,a_i), -(b_i,t), +(t,z_i), +(z_i,t)}
-__device__ __forceinline__ void apply_entry(DevState *st, u64 *tkey, u64 *tmeta, u64 cap, u32 e, int32_t d, u32 VS, u32 z0, int *s_dD,
-                                            int *s_occ)
+// token t holds {-(t,a_i), -(b_i,t), +(t,z_i), +(z_i,t)}.
+// Every update is a chain of dependent, cache-missing accesses (probe the key, then the atomic on its count; the
+// table has long outgrown L2), so the chains of up to N entries are started together: all first probes are issued
+// before any of them is waited for.
+struct EntryProbe
+{
+    u64 key, s, k; // pair key, first probe slot, key found there
+    u32 h, vec;
+};
+__device__ __forceinline__ void entry_probe(const DevState *st, const u64 *tkey, u64 cap, u32 e, u32 VS, u32 z0, EntryProbe &p)
 {
     const u32 bi = e / (4 * VS), r = e - bi * 4 * VS;
     const u32 a = st->ba[bi], b = st->bb[bi], z = z0 + bi;
     const u32 t = r >> 2, vec = r & 3u;
-    u32 ka, kb;
-    if (vec == 0)
+    const u32 ka = (vec == 1) ? b : ((vec == 3) ? z : t);
+    const u32 kb = (vec == 0) ? a : ((vec == 2) ? z : t);
+    p.key = (u64)ka | ((u64)kb << 32);
+    p.h = murmur3_pair(ka, kb);
+    p.vec = vec;
+    p.s = probe_start(p.h, cap);
+    p.k = tkey[p.s];
+}
+__device__ __forceinline__ void entry_finish(DevState *st, u64 *tkey, u64 *tmeta, u64 cap, const EntryProbe &p, u32 d, int *s_dD, int *s_occ)
+{
+    u64 s = p.s, k = p.k;
+    if (p.vec >= 2)
     {
-        ka = t;
-        kb = a;
-    }
-    else if (vec == 1)
-    {
-        ka = b;
-        kb = t;
-    }
-    else if (vec == 2)
-    {
-        ka = t;
-        kb = z;
-    }
-    else
-    {
-        ka = z;
-        kb = t;
-    }
-    const u64 key = (u64)ka | ((u64)kb << 32);
-    const u32 h = murmur3_pair(ka, kb);
-    if (vec >= 2)
-    {
-        const u64 s = table_insert_counted(st, tkey, tmeta, cap, key, h, s_occ);
-        if (s == NO_SLOT)
+        // a pair that contains a new id: claim a slot if it is not in the table yet
+        bool found = false;
+        for (u64 i = 0; i < cap; i++)
+        {
+            if (k == EMPTY_KEY)
+            {
+                k = atomicCAS(tkey + s, EMPTY_KEY, p.key);
+                if (k == EMPTY_KEY)
+                {
+                    *hsh_ptr(tmeta, s) = p.h;
+                    atomicAdd(s_occ, 1);
+                    k = p.key;
+                }
+            }
+            if (k == p.key)
+            {
+                found = true;
+                break;
+            }
+            s = (s + 1) & (cap - 1);
+            k = tkey[s];
+        }
+        if (!found)
         {
             atomicOr(&st->err, ERR_TABLE_FULL);
             return;
         }
-        const u32 old = atomicAdd(cnt_ptr(tmeta, s), (u32)d);
+        const u32 old = atomicAdd(cnt_ptr(tmeta, s), d);
         if (old == 0)
             atomicAdd(s_dD, 1);
-        cand_offer(st, s, old + (u32)d);
+        cand_offer(st, s, old + d);
     }
     else
     {
-        const u64 s = table_find(tkey, cap, key, h);
-        if (s == NO_SLOT)
+        bool found = false;
+        for (u64 i = 0; i < cap; i++)
+        {
+            if (k == p.key)
+            {
+                found = true;
+                break;
+            }
+            if (k == EMPTY_KEY)
+                break;
+            s = (s + 1) & (cap - 1);
+            k = tkey[s];
+        }
+        if (!found)
         {
             atomicOr(&st->err, ERR_MISSING_KEY);
             return;
         }
-        const u32 old = atomicSub(cnt_ptr(tmeta, s), (u32)d);
-        if (old < (u32)d)
+        const u32 old = atomicSub(cnt_ptr(tmeta, s), d);
+        if (old < d)
             atomicOr(&st->err, ERR_NEGATIVE);
-        if (old == (u32)d)
+        if (old == d)
             atomicAdd(s_dD, -1);
     }
+}
+template <int N>
+__device__ __forceinline__ void apply_entries(DevState *st, u64 *tkey, u64 *tmeta, u64 cap, const u32 (&e)[N], const u32 (&d)[N], u32 VS,
+                                              u32 z0, int *s_dD, int *s_occ)
+{
+    EntryProbe p[N];
+#pragma unroll
+    for (int j = 0; j < N; j++)
+        if (d[j])
+            entry_probe(st, tkey, cap, e[j], VS, z0, p[j]);
+#pragma unroll
+    for (int j = 0; j < N; j++)
+        if (d[j])
+            entry_finish(st, tkey, tmeta, cap, p[j], d[j], s_dD, s_occ);
 }
 
 // This rank's own deltas: fold them into the table, clear them, and (several GPUs: `xch`) push every non-zero
 // counter as one (index, value) entry into my slot of every peer's inbox.  Integer adds commute, so every replica
 // of the table ends up with the sum over all ranks whatever order the lists are folded in; D is kept exact by the
 // 0 <-> non-0 transitions of the individual adds (a pass never adds to and subtracts from the same key: additions
-// go to pairs that contain a new id).
-__device__ inline void apply_deltas(DevState *st, int32_t *delta, u32 gtid, u32 gsize, bool xch, u32 xpar)
+// go to pairs that contain a new id).  A thread takes one token's four counters (one 128-bit load) per trip.
+__device__ __noinline__ void apply_deltas(DevState *st, int32_t *delta, u32 gtid, u32 gsize, bool xch, u32 xpar)
 {
     __shared__ int s_dD, s_occ;
     if (threadIdx.x == 0)
@@ -1662,7 +1689,7 @@ __device__ inline void apply_deltas(DevState *st, int32_t *delta, u32 gtid, u32 
     __syncthreads();
     const u32 nb = st->nb, z0 = st->z;
     const u32 VS = z0 + nb;
-    const u32 total = nb * 4 * VS;
+    const u32 quads = nb * VS;
     u64 *tmeta = st->tmeta, *tkey = st->tkey;
     const u64 cap = st->tcap;
     if (gtid + nb >= gsize && gtid < gsize)
@@ -1680,39 +1707,51 @@ __device__ inline void apply_deltas(DevState *st, int32_t *delta, u32 gtid, u32 
     }
     const u32 lane = threadIdx.x & 31u, me = st->rank, P = st->world;
     const u64 xcap = st->x.xcap;
-    for (u32 e0 = gtid - lane; e0 < total; e0 += gsize) // (warp-uniform trip count: the list positions come from a ballot)
+    int4 *dq = reinterpret_cast<int4 *>(delta + HDR_INTS);
+    for (u32 q0 = gtid - lane; q0 < quads; q0 += gsize) // (warp-uniform trip count: the list positions come from a warp scan)
     {
-        const u32 e = e0 + lane;
-        const int32_t d = (e < total) ? delta[HDR_INTS + e] : 0;
-        if (d)
-            delta[HDR_INTS + e] = 0;
-        if (xch)
+        const u32 q = q0 + lane;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (q < quads)
+            v = __ldcg(dq + q);
+        const u32 d[4] = {(u32)v.x, (u32)v.y, (u32)v.z, (u32)v.w};
+        const u32 e[4] = {4 * q, 4 * q + 1, 4 * q + 2, 4 * q + 3};
+        const u32 c = (d[0] ? 1u : 0u) + (d[1] ? 1u : 0u) + (d[2] ? 1u : 0u) + (d[3] ? 1u : 0u);
+        if (c)
+            dq[q] = make_int4(0, 0, 0, 0);
+        if (xch && __any_sync(0xFFFFFFFFu, c != 0))
         {
-            const u32 mask = __ballot_sync(0xFFFFFFFFu, d != 0);
-            if (mask)
+            u32 incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
             {
-                const int leader = __ffs(mask) - 1;
-                u32 base = 0;
-                if ((int)lane == leader)
-                    base = atomicAdd(&st->x_count, (u32)__popc(mask));
-                base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                if (d)
+                const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if ((int)lane >= o)
+                    incl += t;
+            }
+            u32 base = 0;
+            if (lane == 31)
+                base = atomicAdd(&st->x_count, incl);
+            base = __shfl_sync(0xFFFFFFFFu, base, 31);
+            u64 pos = (u64)base + incl - c;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (d[j])
                 {
-                    const u64 pos = (u64)base + (u32)__popc(mask & ((1u << lane) - 1u));
                     if (pos < xcap)
                     {
-                        const u64 pk = (u64)e | ((u64)(u32)d << 32);
+                        const u64 pk = (u64)e[j] | ((u64)d[j] << 32);
                         for (u32 p = 0; p < P; p++)
                             if (p != me)
                                 xchg_entries(st->x.peer[p], xcap, xpar, me)[pos] = pk; // store into the peer's HBM over NVLink
                     }
                     else
                         atomicOr(&st->err, ERR_XCHG_OVERFLOW);
+                    pos++;
                 }
-            }
         }
-        if (d)
-            apply_entry(st, tkey, tmeta, cap, e, d, VS, z0, &s_dD, &s_occ);
+        if (c)
+            apply_entries<4>(st, tkey, tmeta, cap, e, d, VS, z0, &s_dD, &s_occ);
     }
     __syncthreads();
     if (threadIdx.x == 0)
@@ -1726,7 +1765,7 @@ __device__ inline void apply_deltas(DevState *st, int32_t *delta, u32 gtid, u32 
 
 // The peers' lists for exchange `seq`, as they arrive in my inbox (starting with the right-hand neighbour so that
 // the ranks do not all wait for the same sender first).
-__device__ inline void apply_peer_lists(DevState *st, u32 gtid, u32 gsize, u32 seq)
+__device__ __noinline__ void apply_peer_lists(DevState *st, u32 gtid, u32 gsize, u32 seq)
 {
     __shared__ int s_dD, s_occ;
     __shared__ u32 s_cnt;
@@ -1749,10 +1788,12 @@ __device__ inline void apply_peer_lists(DevState *st, u32 gtid, u32 gsize, u32 s
         __syncthreads();
         const u32 cnt = s_cnt;
         const u64 *ent = xchg_entries(st->x.local, xcap, par, sender);
-        for (u32 i = gtid; i < cnt; i += gsize)
+        for (u32 i = gtid; i < cnt; i += 2 * gsize)
         {
-            const u64 pk = ld_relaxed_sys_u64(ent + i); // written by the peer: not through this SM's L1
-            apply_entry(st, tkey, tmeta, cap, (u32)pk, (int32_t)(u32)(pk >> 32), VS, z0, &s_dD, &s_occ);
+            // (written by the peer: not through this SM's L1)
+            const u64 p0 = ld_relaxed_sys_u64(ent + i), p1 = (i + gsize < cnt) ? ld_relaxed_sys_u64(ent + i + gsize) : 0ull;
+            const u32 e[2] = {(u32)p0, (u32)p1}, d[2] = {(u32)(p0 >> 32), (u32)(p1 >> 32)};
+            apply_entries<2>(st, tkey, tmeta, cap, e, d, VS, z0, &s_dD, &s_occ);
         }
     }
     __syncthreads();

@@ -251,6 +251,248 @@ __device__ __forceinline__ bool iter_bits_multi(const u32 *sin, int j, int lane,
     return true;
 }
 
+// ---- a == b on a RANGED stream ---------------------------------------------------------------------------------
+// `aaaa -> z z`: replacements pair up from the start of each run of a (bpe.c:760-772 is greedy left to right), so a
+// position starts one iff it holds a, its right neighbour holds a, and the number of a right in front of it is
+// even.  That parity crosses tiles, ranges and shards, which the warp-specialised pipeline below (every 128-token
+// iteration scanned independently) cannot carry; a == b merges are rare (under 1 % of merges on the Zipf corpora),
+// so they take this plain path in the same launch instead of pausing the loop for a repack -> dense kernel ->
+// re-partition detour (round 1: 5-8 % of a run).  One CTA per range as in the streaming path, tiles one after the
+// other (the parity and the output offset are running values of the CTA), every range compacted in place.
+//   across ranges: every CTA first publishes the parity of the run that ends its INPUT range (st->rpar, stamped
+//                  with the merge epoch) and reads the ranges in front of it as far as the run reaches (all CTAs of
+//                  the grid are resident: one per range, two per SM);
+//   across shards: st->carry_in, derived from the peers' edge records (resolve_edges).
+// The pair-count deltas follow replace_kernel's rules for a == b (each pair INSTANCE charged once).
+constexpr int SP_ITEMS = 8, SP_THREADS = V_TILE / SP_ITEMS; // 512 of the CTA's threads hold 8 tokens each
+__device__ __noinline__ void same_pair_range(DevState *st, int32_t *gdelta, u32 *smem)
+{
+    const u32 a = st->a, z = st->z, cta = blockIdx.x, nr = st->nr, epoch = st->epoch;
+    const u32 ibuf = st->cur, obuf = st->cur ^ 1u;
+    const u64 rcap = st->rcap;
+    const u32 n = st->rcnt[ibuf][cta];
+    const u32 *in = st->tok[ibuf] + (u64)cta * rcap;
+    u32 *out = st->tok[obuf] + (u64)cta * rcap;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    u32 *s_tok = smem + 4; // s_tok[p] = token at tile position p, p in [-2, V_TILE + 3)
+    __shared__ u32 s_halo[5], s_carry, s_warp[V_THREADS / 32], s_tail[2];
+    const u32 *cnt = st->rcnt[ibuf], *ed = st->redge[ibuf];
+    if (cta == 0 && tid == 0)
+        st->layout_next = LAYOUT_RANGED;
+    if (warp == 0)
+    {
+        // parity of the run of equal tokens that ends my input range (whatever the token: it only matters if it is a)
+        u32 run = 0;
+        bool uniform = true;
+        if (n)
+        {
+            const u32 last = in[n - 1];
+            u32 pos = n;
+            while (pos > 0)
+            {
+                const int i = (int)pos - 1 - lane;
+                const bool eq = (i >= 0) && (in[i] == last);
+                const u32 m = __ballot_sync(0xFFFFFFFFu, eq);
+                const int c = (m == 0xFFFFFFFFu) ? 32 : (__ffs(~m) - 1);
+                run += (u32)c;
+                pos -= (u32)c;
+                if (c < 32)
+                    break;
+            }
+            uniform = (run == n);
+        }
+        if (lane == 0)
+        {
+            *reinterpret_cast<volatile u32 *>(&st->rpar[cta]) = (epoch << 2) | ((u32)uniform << 1) | (run & 1u);
+            __threadfence();
+            // halos: the two tokens in front of my range and the three behind it (as in the streaming path)
+            u32 near[2];
+            int got = 0;
+            for (int q = (int)cta - 1; q >= 0 && got < 2; q--)
+            {
+                if (cnt[q] >= 1 && got < 2)
+                    near[got++] = ed[q * EDGE_WORDS + 4];
+                if (cnt[q] >= 2 && got < 2)
+                    near[got++] = ed[q * EDGE_WORDS + 3];
+            }
+            s_halo[1] = got >= 1 ? near[0] : st->halo_before[1];
+            s_halo[0] = got >= 2 ? near[1] : (got == 1 ? st->halo_before[1] : st->halo_before[0]);
+            got = 0;
+            for (u32 q = cta + 1; q < nr && got < 3; q++)
+                for (u32 k = 0; k < 3 && k < cnt[q] && got < 3; k++)
+                    s_halo[2 + got++] = ed[q * EDGE_WORDS + k];
+            for (int k = 0; got < 3; k++)
+                s_halo[2 + got++] = st->halo_after[k];
+            // parity of the number of a right in front of my range: back through the ranges while the run goes on
+            u32 acc = 0;
+            bool open = (s_halo[1] == a);
+            int q = (int)cta - 1;
+            while (open && q >= 0)
+            {
+                if (cnt[q] == 0)
+                {
+                    q--;
+                    continue;
+                }
+                u32 v;
+                do
+                {
+                    v = *reinterpret_cast<volatile u32 *>(&st->rpar[q]);
+                } while ((v >> 2) != (epoch & 0x3FFFFFFFu));
+                acc ^= v & 1u;
+                open = (v & 2u) != 0;
+                q--;
+            }
+            if (open) // the run reaches the start of the shard: the neighbouring GPU's part of it
+                acc ^= st->carry_in & 1u;
+            s_carry = acc;
+        }
+    }
+    __syncthreads();
+    u32 carry = s_carry; // parity of the number of a right in front of the current tile
+    u32 out_off = 0;
+    const u32 ntiles = (n + V_TILE - 1) / V_TILE;
+    for (u32 t = 0; t < ntiles; t++)
+    {
+        const u32 base = t * V_TILE;
+        const u32 tl = (n - base < (u32)V_TILE) ? (n - base) : (u32)V_TILE;
+        // ---- stage the tile.  The two tokens in front of it come from the previous tile's copy (their place in the
+        // stream may have been overwritten by that tile's output), the ones behind it have not been touched yet.
+        for (int p = tid; p < V_TILE + 3; p += V_THREADS)
+        {
+            const u32 g = base + (u32)p;
+            s_tok[p] = (g < n) ? in[g] : ((g - n < 3u) ? s_halo[2 + (g - n)] : SENT);
+        }
+        if (tid < 2)
+            s_tok[tid - 2] = (t == 0) ? s_halo[tid] : s_tail[tid];
+        __syncthreads();
+        u32 keep = 0, mm = 0, cntk = 0, ea = 0;
+        u32 w[SP_ITEMS + 5]; // w[k] = token at tile position p0 + k - 2
+        const u32 p0 = (u32)tid * SP_ITEMS;
+        const bool worker = tid < SP_THREADS;
+        if (worker)
+        {
+#pragma unroll
+            for (int k = 0; k < SP_ITEMS + 5; k++)
+                w[k] = s_tok[(int)p0 + k - 2];
+            const u32 valid = (p0 >= tl) ? 0u : ((tl - p0 < (u32)SP_ITEMS) ? (tl - p0) : (u32)SP_ITEMS);
+            const u32 OWNV = ((1u << valid) - 1u) << 2;
+#pragma unroll
+            for (int k = 0; k < SP_ITEMS + 5; k++)
+                ea |= (u32)(w[k] == a) << k;
+            u32 par0 = 0; // parity of the number of a right in front of my first token
+            if (valid > 0 && ((ea >> 1) & 1u))
+            {
+                u32 c = 0;
+                int i = (int)p0 - 1;
+                while (i >= 0 && s_tok[i] == a)
+                {
+                    c++;
+                    i--;
+                }
+                par0 = (i < 0) ? ((c ^ carry) & 1u) : (c & 1u);
+            }
+            u32 m = ((ea >> 1) & (ea >> 2) & 1u & par0) << 1; // does one start at my left neighbour?
+            u32 par = par0;
+#pragma unroll
+            for (int k = 2; k < SP_ITEMS + 2; k++)
+            {
+                const u32 isa = (ea >> k) & 1u;
+                m |= (isa & ((ea >> (k + 1)) & 1u) & (par ^ 1u)) << k;
+                par = isa ? (par ^ 1u) : 0u;
+            }
+            mm = m & OWNV;            // replacements that start on my tokens
+            keep = OWNV & ~(m << 1);  // a token goes away iff one starts at its left neighbour
+            cntk = (u32)__popc(keep);
+        }
+        // the carry for the next tile, and this tile's last two tokens, before the tile is overwritten
+        if (tid == V_THREADS - 1)
+        {
+            u32 c = 0;
+            int i = (int)tl - 1;
+            while (i >= 0 && s_tok[i] == a)
+            {
+                c++;
+                i--;
+            }
+            s_carry = (i < 0) ? ((c ^ carry) & 1u) : (c & 1u);
+            s_tail[0] = s_tok[(int)tl - 2];
+            s_tail[1] = s_tok[(int)tl - 1];
+        }
+        // ---- block-wide exclusive scan of the kept counts
+        u32 incl = cntk;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const u32 v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o)
+                incl += v;
+        }
+        if (lane == 31)
+            s_warp[warp] = incl;
+        __syncthreads(); // every thread has read its window: s_tok may now be overwritten
+        u32 woff = 0, total = 0;
+#pragma unroll
+        for (int i = 0; i < V_THREADS / 32; i++)
+        {
+            const u32 v = s_warp[i];
+            woff += (i < warp) ? v : 0u;
+            total += v;
+        }
+        carry = s_carry;
+        if (worker)
+        {
+            u32 r = woff + incl - cntk;
+#pragma unroll
+            for (int k = 2; k < SP_ITEMS + 2; k++)
+                if ((keep >> k) & 1u)
+                    s_tok[r++] = ((mm >> k) & 1u) ? z : w[k];
+            // ---- pair-count deltas (replace_kernel's rules for a == b)
+            if (mm)
+            {
+#pragma unroll
+                for (int k = 2; k < SP_ITEMS + 2; k++)
+                    if ((mm >> k) & 1u)
+                    {
+                        const u32 x = w[k - 1], y = w[k + 2];
+                        const u32 pm = (ea >> (k - 1)) & 1u;                      // a replacement ends right in front
+                        const u32 nm = (ea >> (k + 2)) & (ea >> (k + 3)) & 1u;    // another one starts right behind
+                        if (x != SENT)
+                        {
+                            if (x != a)
+                                delta_add(st, gdelta, (u64)x * 4 + 0, 1);
+                            delta_add(st, gdelta, (u64)(pm ? z : x) * 4 + 2, 1);
+                        }
+                        if (y != SENT && !nm)
+                        {
+                            if (y != a)
+                                delta_add(st, gdelta, (u64)y * 4 + 1, 1);
+                            delta_add(st, gdelta, (u64)y * 4 + 3, 1);
+                        }
+                    }
+            }
+        }
+        __syncthreads();
+        for (u32 i = tid; i < total; i += V_THREADS)
+            out[out_off + i] = s_tok[i];
+        out_off += total;
+        __syncthreads();
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+        __threadfence_block();
+        u32 *oe = st->redge[obuf] + cta * EDGE_WORDS;
+        const volatile u32 *o = out;
+        for (u32 k = 0; k < 3; k++)
+            oe[k] = (k < out_off) ? o[k] : SENT;
+        oe[3] = out_off >= 2 ? o[out_off - 2] : SENT;
+        oe[4] = out_off >= 1 ? o[out_off - 1] : SENT;
+        st->rcnt[obuf][cta] = out_off;
+        atomicAdd(&st->n_next, (u64)out_off);
+    }
+}
+
 template <bool SMEM_HIST>
 __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *st, int32_t *delta, u32 hist_words)
 {
@@ -275,21 +517,26 @@ __global__ void __launch_bounds__(V_THREADS, 2) replace_stream_kernel(DevState *
         return;
     }
     const u32 cta = blockIdx.x, nr = st->nr;
-    if (a == b || st->layout != LAYOUT_RANGED)
+    if (st->layout != LAYOUT_RANGED)
     {
         if (threadIdx.x == 0)
-            atomicOr(&st->err, ERR_PROBE); // host logic error: this kernel only takes a != b passes of a RANGED stream
+            atomicOr(&st->err, ERR_PROBE); // host logic error: this kernel only takes passes of a RANGED stream
         return;
     }
     if (cta >= nr)
         return;
+    extern __shared__ __align__(16) u32 smem[];
+    if (a == b)
+    {
+        same_pair_range(st, delta + HDR_INTS, smem);
+        return;
+    }
     const u32 ibuf = st->cur, obuf = st->cur ^ 1u;
     const u64 rcap = st->rcap;
     const u32 n = st->rcnt[ibuf][cta]; // tokens of my range
     if (cta == 0 && threadIdx.x == 0)
         st->layout_next = LAYOUT_RANGED;
 
-    extern __shared__ __align__(16) u32 smem[];
     u32 *s_in = smem;                                       // NST x V_STAGE_WORDS
     u32 *s_staging = smem + NST * V_STAGE_WORDS;       // V_STORE_WARPS x V_STAGING_WORDS
     int32_t *s_hist = reinterpret_cast<int32_t *>(s_staging + V_STORE_WARPS * V_STAGING_WORDS);
