@@ -407,6 +407,7 @@ def bench_engine(args, w, rank, world, local):
         tw = WORKLOADS[w["table"]]
         _, tshard = make_shard(tw, rank, world)
         ctx.upload_ptr(tshard.ctypes.data, tshard.size)
+        barrier(world)
         ctx.train(tw["merges"])
         table, _ = ctx.download(tokens=False)
         del tshard
@@ -414,6 +415,7 @@ def bench_engine(args, w, rank, world, local):
     pin_t, shard = make_shard(w, rank, world)
     n = w["size"]
     ctx.upload_ptr(shard.ctypes.data, shard.size)
+    barrier(world)   # (the ranks generate their shards at different speeds)
 
     if encode_mode:
         run = lambda: ctx.encode(table)

@@ -589,14 +589,16 @@ __device__ inline void xchg_signal(DevState *st, u32 seq, u32 count)
 // one thread: wait until `sender` has raised its flag for exchange `seq` in my inbox.  Peers run the same launch
 // sequence on their own GPUs; a flag that does not arrive within x_timeout_ns (20 s) means a rank died or fell out of step:
 // the run is stopped with an error instead of spinning for ever.
-__device__ inline bool xchg_wait(DevState *st, u32 sender, u32 seq)
+__device__ inline bool xchg_wait(DevState *st, u32 sender, u32 seq, u64 timeout_ns = 0)
 {
+    if (!timeout_ns)
+        timeout_ns = st->x_timeout_ns;
     const u32 *f = st->x.local + XCHG_FLAGS + sender;
     const u64 t0 = gtime();
     u32 spins = 0;
     while ((int)(ld_acquire_sys(f) - seq) < 0)
     {
-        if ((++spins & 1023u) == 0 && gtime() - t0 > st->x_timeout_ns)
+        if ((++spins & 1023u) == 0 && gtime() - t0 > timeout_ns)
         {
             atomicOr(&st->err, ERR_XCHG_TIMEOUT);
             st->stop = STOP_ERROR;
@@ -621,9 +623,11 @@ __global__ void edge_exchange_kernel(DevState *st, int use_next)
         __threadfence_system();
         xchg_signal(st, seq, 0u);
         bool ok = true;
+        // (the ranks of a job start their runs when their callers get there - corpus generation, file reads - not in
+        // lockstep: the first exchange of a run waits 30 times longer than the per-pass ones)
         for (u32 p = 0; p < st->world && ok; p++)
             if (p != st->rank)
-                ok = xchg_wait(st, p, seq);
+                ok = xchg_wait(st, p, seq, 30 * st->x_timeout_ns);
         st->xseq = seq;
     }
 }
@@ -1060,6 +1064,13 @@ __device__ inline void decide(DevState *st, u64 k, u64 s, u32 m, const u32 *rec_
 __device__ inline void decide_rank(DevState *st, const u32 *rec_all)
 {
     const u64 r = st->merges_done;
+    if (st->world > 1)
+    {
+        u64 total = 0; // (kept current for the statistics of a run that ends here)
+        for (u32 q = 0; q < st->world; q++)
+            total += (u64)rec_all[q * REC_INTS] | ((u64)rec_all[q * REC_INTS + 1] << 32);
+        st->n_global = total;
+    }
     if (r >= st->enc_total)
     {
         st->stop = STOP_DONE;
