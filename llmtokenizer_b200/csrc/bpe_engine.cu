@@ -574,6 +574,12 @@ static size_t replace_smem_bytes(bool hist, u32 z) { return (R_TILE + 8) * sizeo
 
 static int setup_kernels(bpe_cuda_ctx *c)
 {
+    {
+        u64 thr[THR_ENTRIES];
+        for (int i = 0; i < THR_ENTRIES; i++)
+            thr[i] = resize_threshold_exact(1ull << (THR_LOG2_MIN + i));
+        CU(cudaMemcpyToSymbol(c_resize_thr, thr, sizeof thr));
+    }
     CU(cudaFuncSetAttribute(replace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(replace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CU(cudaFuncSetAttribute(widen_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));

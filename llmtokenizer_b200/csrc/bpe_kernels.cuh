@@ -161,7 +161,7 @@ struct DevState
     u32 rank, world;
     // peer-memory exchange (world > 1): sequence number of the last exchange this rank completed, scratch counters
     Xchg x;
-    u32 xseq, x_count, x_done, x_pad;
+    u32 xseq, x_count, x_done, x_bar;
     u64 x_timeout_ns; // how long a rank waits for a peer's flag before it stops the run with an error
     // the reference's 16 worker tables keep their grown bucket count across iterations
     u64 bt[REF_THREADS];
@@ -242,7 +242,7 @@ __host__ __device__ __forceinline__ bool resize_due(u64 nodes, u64 buckets)
 {
     return (double)nodes >= 0.3 * (double)buckets;
 }
-__host__ __device__ inline u64 resize_threshold(u64 buckets)
+__host__ __device__ inline u64 resize_threshold_exact(u64 buckets)
 {
     u64 t = (u64)(0.3 * (double)buckets);
     while (!resize_due(t, buckets))
@@ -250,6 +250,20 @@ __host__ __device__ inline u64 resize_threshold(u64 buckets)
     while (t > 0 && resize_due(t - 1, buckets))
         t--;
     return t;
+}
+// Every table of the reference has a power-of-two bucket count (256 * 2^j workers, 65,536 * 2^k merged), and the
+// selection asks for thresholds on its critical path (bucket order B(D), the exact-threshold edge, batch margins):
+// on the device they come from a table filled once by the host with the function above.
+constexpr int THR_LOG2_MIN = 8, THR_ENTRIES = 48;
+__constant__ u64 c_resize_thr[THR_ENTRIES];
+__host__ __device__ inline u64 resize_threshold(u64 buckets)
+{
+#ifdef __CUDA_ARCH__
+    const int lg = 63 - __clzll((long long)buckets);
+    if ((buckets & (buckets - 1)) == 0 && lg >= THR_LOG2_MIN && lg < THR_LOG2_MIN + THR_ENTRIES)
+        return c_resize_thr[lg - THR_LOG2_MIN];
+#endif
+    return resize_threshold_exact(buckets);
 }
 // bucket count of the merged table (fresh 65,536 buckets every iteration, bpe.c:611,684) once D
 // keys went in, away from the exact-threshold edge (handled by the resolver)
@@ -1684,12 +1698,86 @@ __device__ __forceinline__ void apply_entries(DevState *st, u64 *tkey, u64 *tmet
             entry_finish(st, tkey, tmeta, cap, p[j], d[j], s_dD, s_occ);
 }
 
-// This rank's own deltas: fold them into the table, clear them, and (several GPUs: `xch`) push every non-zero
-// counter as one (index, value) entry into my slot of every peer's inbox.  Integer adds commute, so every replica
-// of the table ends up with the sum over all ranks whatever order the lists are folded in; D is kept exact by the
-// 0 <-> non-0 transitions of the individual adds (a pass never adds to and subtracts from the same key: additions
-// go to pairs that contain a new id).  A thread takes one token's four counters (one 128-bit load) per trip.
-__device__ __noinline__ void apply_deltas(DevState *st, int32_t *delta, u32 gtid, u32 gsize, bool xch, u32 xpar)
+// Several GPUs, step 1 of a pass's exchange: push every non-zero counter of this rank's delta vectors as one
+// (index, value) entry into my slot of every peer's inbox (the counters themselves stay where they are).
+__device__ __noinline__ void push_deltas(DevState *st, const int32_t *delta, u32 gtid, u32 gsize, u32 xpar)
+{
+    const u32 nb = st->nb, z0 = st->z;
+    const u32 quads = nb * (z0 + nb);
+    const u32 lane = threadIdx.x & 31u, me = st->rank, P = st->world;
+    const u64 xcap = st->x.xcap;
+    const int4 *dq = reinterpret_cast<const int4 *>(delta + HDR_INTS);
+    for (u32 q0 = gtid - lane; q0 < quads; q0 += gsize) // (warp-uniform trip count: the list positions come from a warp scan)
+    {
+        const u32 q = q0 + lane;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (q < quads)
+            v = __ldcg(dq + q);
+        const u32 d[4] = {(u32)v.x, (u32)v.y, (u32)v.z, (u32)v.w};
+        const u32 c = (d[0] ? 1u : 0u) + (d[1] ? 1u : 0u) + (d[2] ? 1u : 0u) + (d[3] ? 1u : 0u);
+        if (!__any_sync(0xFFFFFFFFu, c != 0))
+            continue;
+        u32 incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if ((int)lane >= o)
+                incl += t;
+        }
+        u32 base = 0;
+        if (lane == 31)
+            base = atomicAdd(&st->x_count, incl);
+        base = __shfl_sync(0xFFFFFFFFu, base, 31);
+        u64 pos = (u64)base + incl - c;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (d[j])
+            {
+                if (pos < xcap)
+                {
+                    const u64 pk = (u64)(4 * q + j) | ((u64)d[j] << 32);
+                    for (u32 p = 0; p < P; p++)
+                        if (p != me)
+                            xchg_entries(st->x.peer[p], xcap, xpar, me)[pos] = pk; // store into the peer's HBM over NVLink
+                }
+                else
+                    atomicOr(&st->err, ERR_XCHG_OVERFLOW);
+                pos++;
+            }
+    }
+}
+
+// Several GPUs, step 2: add the peers' lists for exchange `seq` to my own delta vectors as they arrive in my inbox
+// (starting with the right-hand neighbour so that the ranks do not all wait for the same sender first).  The
+// vectors are L2-resident, so this is cheap; folding every list into the (cache-missing) pair table separately
+// would cost P times the table accesses.  Afterwards the vectors hold the sum over all ranks - the same numbers on
+// every rank - and apply_deltas() runs exactly as on one GPU.
+__device__ __noinline__ void add_peer_lists(DevState *st, int32_t *delta, u32 gtid, u32 gsize, u32 seq)
+{
+    __shared__ u32 s_cnt;
+    const u64 xcap = st->x.xcap;
+    const u32 me = st->rank, P = st->world, par = seq & 1u;
+    for (u32 k = 1; k < P; k++)
+    {
+        const u32 sender = (me + k) % P;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            s_cnt = xchg_wait(st, sender, seq) ? ld_relaxed_sys_u32(st->x.local + XCHG_COUNTS + par * MAX_RANKS + sender) : 0u;
+        __syncthreads();
+        const u32 cnt = s_cnt;
+        const u64 *ent = xchg_entries(st->x.local, xcap, par, sender);
+        for (u32 i = gtid; i < cnt; i += gsize)
+        {
+            const u64 pk = ld_relaxed_sys_u64(ent + i); // written by the peer: not through this SM's L1
+            atomicAdd(delta + HDR_INTS + (u32)pk, (int32_t)(u32)(pk >> 32));
+        }
+    }
+}
+
+// Fold the delta vectors into the pair table and clear them.  D is kept exact by the 0 <-> non-0 transitions of
+// the individual adds.  A thread takes one token's four counters (one 128-bit load) per trip.
+__device__ __noinline__ void apply_deltas(DevState *st, int32_t *delta, u32 gtid, u32 gsize)
 {
     __shared__ int s_dD, s_occ;
     if (threadIdx.x == 0)
@@ -1716,96 +1804,16 @@ __device__ __noinline__ void apply_deltas(DevState *st, int32_t *delta, u32 gtid
                 atomicAdd(&s_dD, -1);
         }
     }
-    const u32 lane = threadIdx.x & 31u, me = st->rank, P = st->world;
-    const u64 xcap = st->x.xcap;
     int4 *dq = reinterpret_cast<int4 *>(delta + HDR_INTS);
-    for (u32 q0 = gtid - lane; q0 < quads; q0 += gsize) // (warp-uniform trip count: the list positions come from a warp scan)
+    for (u32 q = gtid; q < quads; q += gsize)
     {
-        const u32 q = q0 + lane;
-        int4 v = make_int4(0, 0, 0, 0);
-        if (q < quads)
-            v = __ldcg(dq + q);
+        const int4 v = __ldcg(dq + q);
         const u32 d[4] = {(u32)v.x, (u32)v.y, (u32)v.z, (u32)v.w};
+        if (!(d[0] | d[1] | d[2] | d[3]))
+            continue;
+        dq[q] = make_int4(0, 0, 0, 0);
         const u32 e[4] = {4 * q, 4 * q + 1, 4 * q + 2, 4 * q + 3};
-        const u32 c = (d[0] ? 1u : 0u) + (d[1] ? 1u : 0u) + (d[2] ? 1u : 0u) + (d[3] ? 1u : 0u);
-        if (c)
-            dq[q] = make_int4(0, 0, 0, 0);
-        if (xch && __any_sync(0xFFFFFFFFu, c != 0))
-        {
-            u32 incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1)
-            {
-                const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if ((int)lane >= o)
-                    incl += t;
-            }
-            u32 base = 0;
-            if (lane == 31)
-                base = atomicAdd(&st->x_count, incl);
-            base = __shfl_sync(0xFFFFFFFFu, base, 31);
-            u64 pos = (u64)base + incl - c;
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (d[j])
-                {
-                    if (pos < xcap)
-                    {
-                        const u64 pk = (u64)e[j] | ((u64)d[j] << 32);
-                        for (u32 p = 0; p < P; p++)
-                            if (p != me)
-                                xchg_entries(st->x.peer[p], xcap, xpar, me)[pos] = pk; // store into the peer's HBM over NVLink
-                    }
-                    else
-                        atomicOr(&st->err, ERR_XCHG_OVERFLOW);
-                    pos++;
-                }
-        }
-        if (c)
-            apply_entries<4>(st, tkey, tmeta, cap, e, d, VS, z0, &s_dD, &s_occ);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        if (s_dD)
-            atomicAdd(reinterpret_cast<u64 *>(&st->distinct), (u64)(i64)s_dD);
-        if (s_occ)
-            atomicAdd(&st->occupied, (u64)s_occ);
-    }
-}
-
-// The peers' lists for exchange `seq`, as they arrive in my inbox (starting with the right-hand neighbour so that
-// the ranks do not all wait for the same sender first).
-__device__ __noinline__ void apply_peer_lists(DevState *st, u32 gtid, u32 gsize, u32 seq)
-{
-    __shared__ int s_dD, s_occ;
-    __shared__ u32 s_cnt;
-    if (threadIdx.x == 0)
-    {
-        s_dD = 0;
-        s_occ = 0;
-    }
-    const u32 nb = st->nb, z0 = st->z;
-    const u32 VS = z0 + nb;
-    u64 *tmeta = st->tmeta, *tkey = st->tkey;
-    const u64 cap = st->tcap, xcap = st->x.xcap;
-    const u32 me = st->rank, P = st->world, par = seq & 1u;
-    for (u32 k = 1; k < P; k++)
-    {
-        const u32 sender = (me + k) % P;
-        __syncthreads();
-        if (threadIdx.x == 0)
-            s_cnt = xchg_wait(st, sender, seq) ? ld_relaxed_sys_u32(st->x.local + XCHG_COUNTS + par * MAX_RANKS + sender) : 0u;
-        __syncthreads();
-        const u32 cnt = s_cnt;
-        const u64 *ent = xchg_entries(st->x.local, xcap, par, sender);
-        for (u32 i = gtid; i < cnt; i += 2 * gsize)
-        {
-            // (written by the peer: not through this SM's L1)
-            const u64 p0 = ld_relaxed_sys_u64(ent + i), p1 = (i + gsize < cnt) ? ld_relaxed_sys_u64(ent + i + gsize) : 0ull;
-            const u32 e[2] = {(u32)p0, (u32)p1}, d[2] = {(u32)(p0 >> 32), (u32)(p1 >> 32)};
-            apply_entries<2>(st, tkey, tmeta, cap, e, d, VS, z0, &s_dD, &s_occ);
-        }
+        apply_entries<4>(st, tkey, tmeta, cap, e, d, VS, z0, &s_dD, &s_occ);
     }
     __syncthreads();
     if (threadIdx.x == 0)
@@ -1837,7 +1845,7 @@ __global__ void __launch_bounds__(256) apply_kernel(DevState *st, int32_t *delta
     if (st->stop != STOP_RUN || !st->pending)
         return;
     if (!st->skip)
-        apply_deltas(st, delta, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, false, 0u);
+        apply_deltas(st, delta, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
     __syncthreads();
     if (threadIdx.x == 0)
     {
@@ -1882,6 +1890,19 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
     const u32 nb_apply = gridDim.x - 1; // the last block of the grid only looks up the stream's last pair
     if (blockIdx.x == nb_apply)
     {
+        // While the other blocks fold the deltas in, this one asks for the candidates' table lines: the table has
+        // long outgrown L2 (2 GB on the 1 GB corpus), and the last block's gathers are on the critical path.
+        if (mode == AS_TRAIN && st->cand_T)
+        {
+            const u32 ncp = min(*reinterpret_cast<volatile u32 *>(&st->ncand), min(st->cand_cap, CAND_FIT));
+            const u64 *pm = st->tmeta, *pk = st->tkey;
+            for (u32 i = threadIdx.x; i < ncp; i += blockDim.x)
+            {
+                const u32 sl = __ldcg(st->cand + i);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pm + sl));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pk + sl));
+            }
+        }
         if (xch && threadIdx.x < 32)
         {
             u32 rec[REC_INTS];
@@ -1890,8 +1911,10 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
                 xchg_push_record(st, seq, rec);
         }
     }
+    else if (xch)
+        push_deltas(st, delta, blockIdx.x * blockDim.x + threadIdx.x, nb_apply * blockDim.x, seq & 1u);
     else if (pending && !st->skip)
-        apply_deltas(st, delta, blockIdx.x * blockDim.x + threadIdx.x, nb_apply * blockDim.x, xch, seq & 1u);
+        apply_deltas(st, delta, blockIdx.x * blockDim.x + threadIdx.x, nb_apply * blockDim.x);
     if (xch)
     {
         __syncthreads();
@@ -1907,7 +1930,22 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
             }
         }
         if (blockIdx.x != nb_apply)
-            apply_peer_lists(st, blockIdx.x * blockDim.x + threadIdx.x, nb_apply * blockDim.x, seq);
+        {
+            add_peer_lists(st, delta, blockIdx.x * blockDim.x + threadIdx.x, nb_apply * blockDim.x, seq);
+            // every block has added its share of every list before anybody folds the sums into the table (all
+            // blocks of this grid are resident: at most one per SM, and the pass kernel in front of it is over)
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                __threadfence();
+                atomicAdd(&st->x_bar, 1u);
+                while (*reinterpret_cast<volatile u32 *>(&st->x_bar) < nb_apply)
+                    ;
+                __threadfence();
+            }
+            __syncthreads();
+            apply_deltas(st, delta, blockIdx.x * blockDim.x + threadIdx.x, nb_apply * blockDim.x);
+        }
         else if (threadIdx.x == 0)
         {
             bool ok = true;
@@ -1951,6 +1989,7 @@ __global__ void __launch_bounds__(SEL_THREADS) apply_select_kernel(DevState *st,
     {
         st->sel_done = 0;
         st->xseq = seq;
+        st->x_bar = 0;
         if (pending)
             finish_pass(st);
     }
