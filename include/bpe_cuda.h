@@ -17,6 +17,9 @@
  *   bpe_cuda_decode           bpe/src/bpe.c:341-394 decompress() with resolve_pair() bpe.c:23-92: ids ->
  *   bpe_cuda_ctx_decode*      bytes through the merge list; byte-exact and NUL-safe (explicit lengths
  *                             instead of the reference's NUL-terminated memo strings)
+ *   bpe_cuda_train_file       bpe/src/bpe.c:130-180 (get_file) + :555 (strlen cut) + :580-584 (widen) in front of the
+ *   bpe_cuda_encode_file      path: the file is read in 32 MB pieces through pinned buffers, piece i+1 being read while
+ *   bpe_cuda_ctx_upload_file  piece i is copied to the GPU and the pieces before it are widened and counted there
  *   bpe_cuda_free             free() of compress()'s outputs (main.c:22)
  *   bpe_cuda_last_error       perror/printf diagnostics of bpe.c:133-171,560
  *
@@ -94,6 +97,13 @@ int bpe_cuda_encode(const uint8_t *bytes, size_t n, const bpe_pair_t *merges, si
 int bpe_cuda_decode(const uint32_t *tokens, size_t n_tokens, const bpe_pair_t *merges, size_t n_merges, uint8_t **bytes_out,
                     size_t *n_bytes, bpe_cuda_stats_t *stats);
 
+/* The same two operations on a FILE (what compress(path, ...) does, bpe.c:541-555): bytes after the first 0x00 are
+ * ignored; n_gpus > 1 gives every rank its own byte range of the file to read. */
+int bpe_cuda_train_file(const char *path, uint64_t max_merges, int n_gpus, bpe_pair_t **merges_out, size_t *n_merges,
+                        uint32_t **tokens_out, size_t *n_tokens, bpe_cuda_stats_t *stats);
+int bpe_cuda_encode_file(const char *path, const bpe_pair_t *merges, size_t n_merges, int n_gpus, uint32_t **tokens_out,
+                         size_t *n_tokens, bpe_cuda_stats_t *stats);
+
 void bpe_cuda_free(void *p);
 const char *bpe_cuda_last_error(void);
 int bpe_cuda_device_count(void);
@@ -115,12 +125,22 @@ int bpe_cuda_ctx_upload(bpe_cuda_ctx_t *ctx, const uint8_t *shard, size_t n_shar
 /* Fill the resident shard from a pointer that is already in device memory (no copy through the host). */
 int bpe_cuda_ctx_upload_device(bpe_cuda_ctx_t *ctx, const void *dev_bytes, size_t n_shard);
 
+/* Bytes [offset, offset + max_len) of a file become the resident shard, cut at the first 0x00 (*nul_found says whether
+ * there was one: ranks that hold later parts of the file must then drop theirs, bpe_cuda_ctx_truncate(ctx, 0)).
+ * Chunked, pinned, double-buffered; the shard is widened and its byte pairs counted while later chunks arrive. */
+int bpe_cuda_ctx_upload_file(bpe_cuda_ctx_t *ctx, const char *path, uint64_t offset, uint64_t max_len, size_t *n_shard,
+                             int *nul_found);
+int bpe_cuda_ctx_truncate(bpe_cuda_ctx_t *ctx, size_t n_shard);
+
 int bpe_cuda_ctx_train(bpe_cuda_ctx_t *ctx, uint64_t max_merges, bpe_cuda_stats_t *stats);
 int bpe_cuda_ctx_encode(bpe_cuda_ctx_t *ctx, const bpe_pair_t *merges, size_t n_merges, bpe_cuda_stats_t *stats);
 
 /* Results of the last train/encode on this context. */
 int bpe_cuda_ctx_result_sizes(bpe_cuda_ctx_t *ctx, size_t *n_merges, size_t *n_tokens_local);
 int bpe_cuda_ctx_download(bpe_cuda_ctx_t *ctx, bpe_pair_t *merges, uint32_t *tokens_local);
+/* the same into pageable (malloc'd) memory: 32 MB pieces through two pinned staging buffers, the host copy of one piece
+ * overlapping the DMA of the next */
+int bpe_cuda_ctx_download_pageable(bpe_cuda_ctx_t *ctx, bpe_pair_t *merges, uint32_t *tokens_local);
 /* device pointer to this rank's token stream after the last run (valid until the next run) */
 const uint32_t *bpe_cuda_ctx_device_tokens(bpe_cuda_ctx_t *ctx);
 

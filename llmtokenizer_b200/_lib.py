@@ -32,7 +32,8 @@ EXPORTS = [
     "bpe_cuda_ctx_upload", "bpe_cuda_ctx_upload_device", "bpe_cuda_ctx_train", "bpe_cuda_ctx_encode",
     "bpe_cuda_ctx_result_sizes", "bpe_cuda_ctx_download", "bpe_cuda_ctx_device_tokens", "bpe_cuda_ctx_set_option",
     "bpe_cuda_decode", "bpe_cuda_ctx_decode", "bpe_cuda_ctx_decode_download", "bpe_cuda_ctx_decode_compare",
-    "bpe_cuda_ctx_device_decoded",
+    "bpe_cuda_ctx_device_decoded", "bpe_cuda_train_file", "bpe_cuda_encode_file", "bpe_cuda_ctx_upload_file",
+    "bpe_cuda_ctx_truncate", "bpe_cuda_ctx_download_pageable",
 ]
 
 _lib = None
@@ -54,6 +55,17 @@ def load():
     lib.bpe_cuda_encode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, P(P(C.c_uint32)),
                                     P(C.c_size_t), P(Stats)]
     lib.bpe_cuda_encode.restype = C.c_int
+    lib.bpe_cuda_train_file.argtypes = [C.c_char_p, C.c_uint64, C.c_int, P(P(Pair)), P(C.c_size_t), P(P(C.c_uint32)), P(C.c_size_t),
+                                        P(Stats)]
+    lib.bpe_cuda_train_file.restype = C.c_int
+    lib.bpe_cuda_encode_file.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int, P(P(C.c_uint32)), P(C.c_size_t), P(Stats)]
+    lib.bpe_cuda_encode_file.restype = C.c_int
+    lib.bpe_cuda_ctx_upload_file.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, P(C.c_size_t), P(C.c_int)]
+    lib.bpe_cuda_ctx_upload_file.restype = C.c_int
+    lib.bpe_cuda_ctx_truncate.argtypes = [C.c_void_p, C.c_size_t]
+    lib.bpe_cuda_ctx_truncate.restype = C.c_int
+    lib.bpe_cuda_ctx_download_pageable.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bpe_cuda_ctx_download_pageable.restype = C.c_int
     lib.bpe_cuda_free.argtypes = [C.c_void_p]
     lib.bpe_cuda_free.restype = None
     lib.bpe_cuda_last_error.restype = C.c_char_p

@@ -9,6 +9,7 @@ resident contexts) are keyword arguments / extra functions.
 All heavy lifting happens in libbpe_cuda.so; nothing here computes merges on the CPU.
 """
 import ctypes as C
+import os
 import sys
 
 import numpy as np
@@ -61,6 +62,43 @@ def train(data, max_merges=0, n_gpus=1):
         lib.bpe_cuda_free(merges)
         lib.bpe_cuda_free(tokens)
     return m, t, st.as_dict()
+
+
+def train_file(path, max_merges=0, n_gpus=1):
+    """train() on a file: read in pinned 32 MB pieces that are copied, widened and counted while the next one is read
+    (bpe.c:130-180, 555, 580-584 in front of the merge loop)."""
+    lib = _lib.load()
+    merges = C.POINTER(Pair)()
+    tokens = C.POINTER(C.c_uint32)()
+    nm, nt = C.c_size_t(), C.c_size_t()
+    st = Stats()
+    rc = lib.bpe_cuda_train_file(str(path).encode(), max_merges, n_gpus, C.byref(merges), C.byref(nm), C.byref(tokens), C.byref(nt),
+                                 C.byref(st))
+    if rc:
+        raise BpeCudaError(rc)
+    try:
+        m = _pairs_to_numpy(merges, nm.value)
+        t = np.ctypeslib.as_array(tokens, shape=(nt.value,)).copy() if nt.value else np.zeros(0, np.uint32)
+    finally:
+        lib.bpe_cuda_free(merges)
+        lib.bpe_cuda_free(tokens)
+    return m, t, st.as_dict()
+
+
+def encode_file(path, merges, n_gpus=1):
+    lib = _lib.load()
+    mg = np.ascontiguousarray(np.asarray(merges, dtype=np.uint32).reshape(-1, 2))
+    tokens = C.POINTER(C.c_uint32)()
+    nt = C.c_size_t()
+    st = Stats()
+    rc = lib.bpe_cuda_encode_file(str(path).encode(), mg.ctypes.data, mg.shape[0], n_gpus, C.byref(tokens), C.byref(nt), C.byref(st))
+    if rc:
+        raise BpeCudaError(rc)
+    try:
+        t = np.ctypeslib.as_array(tokens, shape=(nt.value,)).copy() if nt.value else np.zeros(0, np.uint32)
+    finally:
+        lib.bpe_cuda_free(tokens)
+    return t, st.as_dict()
 
 
 def encode(data, merges, n_gpus=1):
@@ -227,13 +265,11 @@ def compress(path, max_merges=0, n_gpus=1):
     merge at 256+k, exactly the dyn_arr the reference returns; None on failure like the reference."""
     if path is None:
         return None
-    try:
-        data = get_file(path)
-    except OSError as e:
-        print(f"fopen: {e.strerror}", file=sys.stderr)  # bpe.c:135
+    if not os.path.isfile(path) or not os.access(path, os.R_OK):
+        print(f"fopen: {os.strerror(2 if not os.path.exists(path) else 13)}", file=sys.stderr)  # bpe.c:135
         return None
     try:
-        merges, ids, _ = train(data, max_merges=max_merges, n_gpus=n_gpus)
+        merges, ids, _ = train_file(path, max_merges=max_merges, n_gpus=n_gpus)
     except BpeCudaError as e:
         if e.rc == -2:
             print("Error: File contains less than 2 characters")  # stdout, bpe.c:560

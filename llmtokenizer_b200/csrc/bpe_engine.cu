@@ -15,10 +15,14 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -123,6 +127,11 @@ struct bpe_cuda_ctx
     // resident input shard
     uint8_t *d_bytes = nullptr;
     size_t bytes_cap = 0, n_bytes = 0;
+    // file ingest / result download: two pinned staging buffers, a copy stream, "buffer is free again" events
+    uint8_t *h_stage[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    bool prewidened = false; // the ingest has already widened and counted the resident shard (consumed by the next run)
     // token stream ping-pong
     u32 *d_tok_alloc[2] = {nullptr, nullptr};
     size_t tok_cap = 0;
@@ -1271,7 +1280,10 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
     CU(cudaMemsetAsync(c->d_delta, 0, c->delta_cap * sizeof(int32_t), c->stream));
     CU(cudaMemsetAsync(c->d_desc, 0, c->desc_cap * sizeof(u64), c->stream));
     CU(cudaMemsetAsync(c->d_pdesc, 0, c->desc_cap * sizeof(u32), c->stream));
-    CU(cudaMemsetAsync(c->d_dense, 0, 65536 * sizeof(u32), c->stream));
+    const bool prewidened = c->prewidened;
+    c->prewidened = false;
+    if (!prewidened)
+        CU(cudaMemsetAsync(c->d_dense, 0, 65536 * sizeof(u32), c->stream));
     if (c->profile_replace && c->prof.empty())
     {
         c->prof.resize(4 * 70000);
@@ -1287,12 +1299,12 @@ static int run_common(bpe_cuda_ctx *c, u64 max_merges, const bpe_pair_t *enc_mer
     CU(cudaEventCreate(&ev1));
     CU(cudaEventRecord(ev0, c->stream));
 
-    // K0 + K1: widen and count byte pairs
-    if (n)
+    // K0 + K1: widen and count byte pairs (already done chunk by chunk when the shard came in through the file ingest)
+    if (n && !prewidened)
     {
         const u64 nvec = (n + 15) / 16;
         const int grid = (int)std::min<u64>((nvec + 255) / 256, (u64)c->sm_count * 3);
-        widen_count_kernel<<<grid, 256, 128 * 128 * sizeof(u32), c->stream>>>(c->d_bytes, n, c->d_tok_alloc[0] + 4, c->d_dense);
+        widen_count_kernel<<<grid, 256, 128 * 128 * sizeof(u32), c->stream>>>(c->d_bytes, 0, n, c->d_tok_alloc[0] + 4, c->d_dense);
         c->launches++;
     }
     if (c->world > 1)
@@ -1815,6 +1827,14 @@ void bpe_cuda_ctx_destroy(bpe_cuda_ctx_t *c)
     cudaFree(c->d_delta);
     cudaFree(c->d_hello);
     cudaFree(c->d_gather);
+    for (int i = 0; i < 2; i++)
+    {
+        cudaFreeHost(c->h_stage[i]);
+        if (c->stage_ev[i])
+            cudaEventDestroy(c->stage_ev[i]);
+    }
+    if (c->copy_stream)
+        cudaStreamDestroy(c->copy_stream);
     for (void *p : c->x_mapped)
         cudaIpcCloseMemHandle(p);
     for (void *p : c->x_owned)
@@ -1892,6 +1912,7 @@ int bpe_cuda_ctx_upload(bpe_cuda_ctx_t *c, const uint8_t *shard, size_t n)
     CU(cudaMemsetAsync(c->d_bytes + n, 0, c->bytes_cap - n, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->n_bytes = n;
+    c->prewidened = false;
     return 0;
 }
 
@@ -1908,6 +1929,134 @@ int bpe_cuda_ctx_upload_device(bpe_cuda_ctx_t *c, const void *dev, size_t n)
     CU(cudaMemsetAsync(c->d_bytes + n, 0, c->bytes_cap - n, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->n_bytes = n;
+    c->prewidened = false;
+    return 0;
+}
+
+// ---- file ingest (reference get_file bpe.c:130-180, strlen cut bpe.c:555, widen bpe.c:580-584) ----
+constexpr size_t STAGE_BYTES = 32u << 20; // per pinned staging buffer (a multiple of 16)
+
+static int ensure_staging(bpe_cuda_ctx *c)
+{
+    if (c->h_stage[0])
+        return 0;
+    for (int i = 0; i < 2; i++)
+    {
+        CU(cudaMallocHost(&c->h_stage[i], STAGE_BYTES));
+        CU(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
+    }
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    return 0;
+}
+
+// Bytes [offset, offset + max_len) of the file become this context's resident shard, cut at the first 0x00 like the
+// reference's strlen (bpe.c:555).  The file is read in 32 MB pieces into two pinned buffers: while piece i+1 is being
+// read, piece i travels to the GPU on a copy stream and the pieces in front of it are widened to tokens and counted
+// (widen_count_kernel on [lo, hi)), so the next train / encode starts from a stream that is already widened and counted.
+int bpe_cuda_ctx_upload_file(bpe_cuda_ctx_t *c, const char *path, uint64_t offset, uint64_t max_len, size_t *n_shard, int *nul_found)
+{
+    if (!c || !path)
+        return BPE_CUDA_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0)
+    {
+        set_error("fopen: %s", strerror(errno)); // bpe.c:133-137
+        return BPE_CUDA_ERR_ARG;
+    }
+    struct stat sb;
+    if (fstat(fd, &sb) != 0)
+    {
+        set_error("fstat: %s", strerror(errno));
+        close(fd);
+        return BPE_CUDA_ERR_ARG;
+    }
+    const u64 fsize = (u64)sb.st_size;
+    const u64 lo = std::min<u64>(offset, fsize), hi = (max_len > fsize - lo) ? fsize : lo + max_len;
+    const size_t want = (size_t)(hi - lo);
+    int rc;
+    auto fail = [&](int r) {
+        close(fd);
+        return r;
+    };
+    if ((rc = ensure_staging(c)) || (rc = ensure_bytes(c, want)) || (rc = ensure_stream_buffers(c, want)))
+        return fail(rc);
+    if (!c->d_dense && cudaMalloc(&c->d_dense, 65536 * sizeof(u32)) != cudaSuccess)
+    {
+        set_error("out of device memory");
+        return fail(BPE_CUDA_ERR_NOMEM);
+    }
+    if (cudaMemsetAsync(c->d_dense, 0, 65536 * sizeof(u32), c->stream) != cudaSuccess)
+        return fail(BPE_CUDA_ERR_CUDA);
+    size_t n = 0;
+    bool nul = false;
+    for (int i = 0; n < want && !nul; i ^= 1)
+    {
+        // buffer i is free again once the copy that last used it is over
+        if (cudaEventSynchronize(c->stage_ev[i]) != cudaSuccess)
+            return fail(BPE_CUDA_ERR_CUDA);
+        const size_t ask = std::min(STAGE_BYTES, want - n);
+        size_t got = 0;
+        while (got < ask)
+        {
+            const ssize_t r = pread(fd, c->h_stage[i] + got, ask - got, (off_t)(lo + n + got));
+            if (r < 0)
+            {
+                set_error("fread: %s", strerror(errno));
+                return fail(BPE_CUDA_ERR_ARG);
+            }
+            if (r == 0)
+                break;
+            got += (size_t)r;
+        }
+        if (got == 0)
+            break;
+        if (const void *z = memchr(c->h_stage[i], 0, got))
+        {
+            got = (size_t)((const uint8_t *)z - c->h_stage[i]);
+            nul = true;
+        }
+        if (got)
+        {
+            if (cudaMemcpyAsync(c->d_bytes + n, c->h_stage[i], got, cudaMemcpyHostToDevice, c->copy_stream) != cudaSuccess ||
+                cudaEventRecord(c->stage_ev[i], c->copy_stream) != cudaSuccess ||
+                cudaStreamWaitEvent(c->stream, c->stage_ev[i], 0) != cudaSuccess)
+                return fail(BPE_CUDA_ERR_CUDA);
+            const u64 nvec = (got + 15) / 16;
+            const int grid = (int)std::min<u64>((nvec + 255) / 256, (u64)c->sm_count * 3);
+            widen_count_kernel<<<grid, 256, 128 * 128 * sizeof(u32), c->stream>>>(c->d_bytes, n, n + got, c->d_tok_alloc[0] + 4, c->d_dense);
+            c->launches++;
+        }
+        n += got;
+        if (got < ask)
+            break;
+    }
+    close(fd);
+    CU(cudaStreamSynchronize(c->copy_stream));
+    CU(cudaMemsetAsync(c->d_bytes + n, 0, c->bytes_cap - n, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    c->n_bytes = n;
+    c->prewidened = (n > 0);
+    if (n_shard)
+        *n_shard = n;
+    if (nul_found)
+        *nul_found = nul ? 1 : 0;
+    return 0;
+}
+
+// (a shard that has to be shortened after the ingest - a lower rank found the corpus' NUL - is widened again by the run)
+int bpe_cuda_ctx_truncate(bpe_cuda_ctx_t *c, size_t n)
+{
+    if (!c || n > c->n_bytes)
+        return BPE_CUDA_ERR_ARG;
+    if (n == c->n_bytes)
+        return 0;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(c->d_bytes + n, 0, c->bytes_cap - n, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->n_bytes = n;
+    c->prewidened = false;
     return 0;
 }
 
@@ -1960,6 +2109,49 @@ int bpe_cuda_ctx_download(bpe_cuda_ctx_t *c, bpe_pair_t *merges, uint32_t *token
         CU(cudaMemcpyAsync(tokens, c->h_st->tok[c->h_st->cur], c->res_n_tokens * sizeof(u32), cudaMemcpyDeviceToHost,
                            c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// The same into PAGEABLE memory (malloc'd results of the one-call entry points): 32 MB pieces
+// through the two pinned staging buffers, the host copy of piece i overlapping the DMA of piece i+1 (a plain
+// cudaMemcpy into pageable memory stages through one small driver buffer and runs at a fraction of the link).
+static int download_staged(bpe_cuda_ctx *c, void *dst, const void *src_dev, size_t bytes)
+{
+    int rc;
+    if ((rc = ensure_staging(c)))
+        return rc;
+    size_t issued = 0, copied = 0, len[2] = {0, 0};
+    int head = 0, next = 0, inflight = 0; // head: the buffer that holds the oldest piece still on its way
+    while (copied < bytes)
+    {
+        while (inflight < 2 && issued < bytes)
+        {
+            len[next] = std::min(STAGE_BYTES, bytes - issued);
+            CU(cudaMemcpyAsync(c->h_stage[next], (const char *)src_dev + issued, len[next], cudaMemcpyDeviceToHost, c->copy_stream));
+            CU(cudaEventRecord(c->stage_ev[next], c->copy_stream));
+            issued += len[next];
+            next ^= 1;
+            inflight++;
+        }
+        CU(cudaEventSynchronize(c->stage_ev[head]));
+        memcpy((char *)dst + copied, c->h_stage[head], len[head]);
+        copied += len[head];
+        head ^= 1;
+        inflight--;
+    }
+    return 0;
+}
+
+int bpe_cuda_ctx_download_pageable(bpe_cuda_ctx_t *c, bpe_pair_t *merges, uint32_t *tokens)
+{
+    if (!c)
+        return BPE_CUDA_ERR_ARG;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    if (merges && c->res_n_merges)
+        CU(cudaMemcpy(merges, c->d_merges, c->res_n_merges * sizeof(bpe_pair_t), cudaMemcpyDeviceToHost));
+    if (tokens && c->res_n_tokens)
+        return download_staged(c, tokens, c->h_st->tok[c->h_st->cur], c->res_n_tokens * sizeof(u32));
     return 0;
 }
 
@@ -2221,18 +2413,49 @@ int bpe_cuda_decode(const uint32_t *tokens, size_t n_tokens, const bpe_pair_t *m
 }
 
 // ---- one-call entry points -------------------------------------------------------------------
+// What the ranks of one call share: meeting points (after the ingest, after the run) and the result buffers.
+struct HostJob
+{
+    int world = 1;
+    std::mutex mu;
+    std::condition_variable cv;
+    int arrived[3] = {0, 0, 0};
+    bool failed = false;
+    std::vector<size_t> rank_bytes, rank_tokens;
+    std::vector<int> rank_nul;
+    u32 *tokens = nullptr;       // malloc'd, all ranks' ids in rank order (the caller free()s it, main.c:22)
+    bpe_pair_t *merges = nullptr; // malloc'd (rank 0's copy)
+    size_t n_merges = 0, total_tokens = 0;
+    // every rank arrives; false if some rank has failed (nobody waits for it any longer)
+    bool meet(int phase)
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        arrived[phase]++;
+        cv.notify_all();
+        cv.wait(lk, [&] { return failed || arrived[phase] >= world; });
+        return !failed;
+    }
+    void abort()
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        failed = true;
+        cv.notify_all();
+    }
+};
+
 struct RankJob
 {
     int rank, world, rc;
-    const uint8_t *bytes;
+    HostJob *job;
+    const uint8_t *bytes; // host shard, or
+    const char *path;     // the file and this rank's byte range of it
+    uint64_t foff, flen;
     size_t n;
     ncclUniqueId id;
     uint64_t max_merges;
     const bpe_pair_t *enc;
     size_t n_enc;
     bool encode;
-    std::vector<bpe_pair_t> merges;
-    std::vector<u32> tokens;
     bpe_cuda_stats_t stats;
     char err[512];
 };
@@ -2249,16 +2472,25 @@ static void rank_main(RankJob *j)
     {
         j->rc = BPE_CUDA_ERR_NOMEM;
         snprintf(j->err, sizeof j->err, "rank %d: %s", j->rank, e.what());
+        j->job->abort();
     }
 }
 
 static void rank_body(RankJob *j)
 {
     bpe_cuda_ctx_t *c = nullptr;
+    HostJob *job = j->job;
     j->err[0] = 0;
     auto fail = [&](int rc) {
         j->rc = rc;
         snprintf(j->err, sizeof j->err, "%s", bpe_cuda_last_error());
+        job->abort();
+        if (c)
+            bpe_cuda_ctx_destroy(c);
+    };
+    auto peer_failed = [&]() {
+        j->rc = BPE_CUDA_ERR_STATE;
+        snprintf(j->err, sizeof j->err, "another rank failed");
         if (c)
             bpe_cuda_ctx_destroy(c);
     };
@@ -2268,7 +2500,25 @@ static void rank_body(RankJob *j)
     if (j->world > 1 && (rc = bpe_cuda_ctx_set_comm(c, j->rank, j->world, &j->id)))
         return fail(rc);
     const auto t0 = std::chrono::steady_clock::now();
-    if ((rc = bpe_cuda_ctx_upload(c, j->bytes, j->n)))
+    if (j->path)
+    {
+        size_t got = 0;
+        int nul = 0;
+        if ((rc = bpe_cuda_ctx_upload_file(c, j->path, j->foff, j->flen, &got, &nul)))
+            return fail(rc);
+        job->rank_bytes[(size_t)j->rank] = got;
+        job->rank_nul[(size_t)j->rank] = nul;
+        if (j->world > 1)
+        {
+            // strlen semantics (bpe.c:555): the corpus ends at the FIRST 0x00 of the file; shards behind it are empty
+            if (!job->meet(0))
+                return peer_failed();
+            for (int q = 0; q < j->rank; q++)
+                if (job->rank_nul[(size_t)q] && (rc = bpe_cuda_ctx_truncate(c, 0)))
+                    return fail(rc);
+        }
+    }
+    else if ((rc = bpe_cuda_ctx_upload(c, j->bytes, j->n)))
         return fail(rc);
     const double ms_h2d = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     rc = j->encode ? bpe_cuda_ctx_encode(c, j->enc, j->n_enc, &j->stats) : bpe_cuda_ctx_train(c, j->max_merges, &j->stats);
@@ -2276,10 +2526,32 @@ static void rank_body(RankJob *j)
         return fail(rc);
     size_t nm = 0, nt = 0;
     bpe_cuda_ctx_result_sizes(c, &nm, &nt);
-    j->merges.resize(nm);
-    j->tokens.resize(nt);
+    job->rank_tokens[(size_t)j->rank] = nt;
+    if (!job->meet(1))
+        return peer_failed();
+    // results go straight into the caller's malloc'd buffers: rank 0 allocates once every rank's size is known
+    if (j->rank == 0)
+    {
+        size_t total = 0;
+        for (size_t v : job->rank_tokens)
+            total += v;
+        job->total_tokens = total;
+        job->n_merges = nm;
+        job->tokens = (u32 *)malloc((total ? total : 1) * sizeof(u32));
+        job->merges = (bpe_pair_t *)malloc((nm ? nm : 1) * sizeof(bpe_pair_t));
+        if (!job->tokens || !job->merges)
+        {
+            set_error("out of host memory");
+            return fail(BPE_CUDA_ERR_NOMEM);
+        }
+    }
+    if (!job->meet(2))
+        return peer_failed();
+    size_t off = 0;
+    for (int q = 0; q < j->rank; q++)
+        off += job->rank_tokens[(size_t)q];
     const auto t1 = std::chrono::steady_clock::now();
-    if ((rc = bpe_cuda_ctx_download(c, j->merges.data(), j->tokens.data())))
+    if ((rc = bpe_cuda_ctx_download_pageable(c, j->rank == 0 ? job->merges : nullptr, job->tokens + off)))
         return fail(rc);
     j->stats.ms_h2d = ms_h2d;
     j->stats.ms_d2h = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
@@ -2287,25 +2559,38 @@ static void rank_body(RankJob *j)
     bpe_cuda_ctx_destroy(c);
 }
 
-static int run_host(const uint8_t *bytes, size_t n_in, uint64_t max_merges, const bpe_pair_t *enc, size_t n_enc, bool encode,
-                    int n_gpus, bpe_pair_t **merges_out, size_t *n_merges, uint32_t **tokens_out, size_t *n_tokens,
+// bytes != NULL: the corpus is in host memory; else `path` names the file it is read from (chunked, pinned, overlapped
+// with the copy and the widening: bpe_cuda_ctx_upload_file)
+static int run_host(const uint8_t *bytes, size_t n_in, const char *path, uint64_t max_merges, const bpe_pair_t *enc, size_t n_enc,
+                    bool encode, int n_gpus, bpe_pair_t **merges_out, size_t *n_merges, uint32_t **tokens_out, size_t *n_tokens,
                     bpe_cuda_stats_t *stats)
 {
-    if (!bytes || !tokens_out || !n_tokens || (!encode && (!merges_out || !n_merges)) || n_gpus < 1 || n_gpus > MAX_RANKS)
+    if ((!bytes && !path) || !tokens_out || !n_tokens || (!encode && (!merges_out || !n_merges)) || n_gpus < 1 || n_gpus > MAX_RANKS)
     {
         set_error("invalid argument");
         return BPE_CUDA_ERR_ARG;
     }
     const auto t0 = std::chrono::steady_clock::now();
     size_t n = 0;
+    if (bytes)
     {
         const void *z = memchr(bytes, 0, n_in); // strlen semantics, bpe.c:555
         n = z ? (size_t)((const uint8_t *)z - bytes) : n_in;
+        if (!encode && n < 2)
+        {
+            set_error("Error: File contains less than 2 characters");
+            return BPE_CUDA_ERR_SHORT;
+        }
     }
-    if (!encode && n < 2)
+    else
     {
-        set_error("Error: File contains less than 2 characters");
-        return BPE_CUDA_ERR_SHORT;
+        struct stat sb;
+        if (stat(path, &sb) != 0)
+        {
+            set_error("fopen: %s", strerror(errno)); // bpe.c:133-137
+            return BPE_CUDA_ERR_ARG;
+        }
+        n = (size_t)sb.st_size; // (the first NUL, if any, is found while the file is read)
     }
     {
         // a rank without a device would fail at once and leave its peers waiting in the communicator setup
@@ -2316,6 +2601,11 @@ static int run_host(const uint8_t *bytes, size_t n_in, uint64_t max_merges, cons
             return BPE_CUDA_ERR_CUDA;
         }
     }
+    HostJob job;
+    job.world = n_gpus;
+    job.rank_bytes.assign((size_t)n_gpus, 0);
+    job.rank_tokens.assign((size_t)n_gpus, 0);
+    job.rank_nul.assign((size_t)n_gpus, 0);
     std::vector<RankJob> jobs((size_t)n_gpus);
     ncclUniqueId id;
     memset(&id, 0, sizeof id);
@@ -2328,12 +2618,22 @@ static int run_host(const uint8_t *bytes, size_t n_in, uint64_t max_merges, cons
     for (int r = 0; r < n_gpus; r++)
     {
         RankJob &j = jobs[(size_t)r];
-        const size_t lo = (size_t)((unsigned __int128)n * (unsigned)r / (unsigned)n_gpus);
-        const size_t hi = (size_t)((unsigned __int128)n * (unsigned)(r + 1) / (unsigned)n_gpus);
+        // (shard borders on multiples of 16 bytes: the ingest widens 16 bytes per thread)
+        size_t lo = (size_t)((unsigned __int128)n * (unsigned)r / (unsigned)n_gpus);
+        size_t hi = (size_t)((unsigned __int128)n * (unsigned)(r + 1) / (unsigned)n_gpus);
+        if (path)
+        {
+            lo = (r == 0) ? 0 : (lo & ~(size_t)15);
+            hi = (r == n_gpus - 1) ? n : (hi & ~(size_t)15);
+        }
         j.rank = r;
         j.world = n_gpus;
         j.rc = -1;
-        j.bytes = bytes + lo;
+        j.job = &job;
+        j.bytes = bytes ? bytes + lo : nullptr;
+        j.path = bytes ? nullptr : path;
+        j.foff = lo;
+        j.flen = hi - lo;
         j.n = hi - lo;
         j.id = id;
         j.max_merges = max_merges;
@@ -2351,41 +2651,28 @@ static int run_host(const uint8_t *bytes, size_t n_in, uint64_t max_merges, cons
         for (auto &t : th)
             t.join();
     }
+    int first_rc = 0;
     for (auto &j : jobs)
-        if (j.rc)
+        if (j.rc && (!first_rc || first_rc == BPE_CUDA_ERR_STATE))
         {
-            set_error("rank %d: %s", j.rank, j.err);
-            return j.rc;
+            set_error(n_gpus > 1 ? "rank %d: %s" : "%.0d%s", n_gpus > 1 ? j.rank : 0, j.err);
+            first_rc = j.rc;
         }
-    size_t total = 0;
-    for (auto &j : jobs)
-        total += j.tokens.size();
-    u32 *toks = (u32 *)malloc((total ? total : 1) * sizeof(u32));
-    if (!toks)
-        return BPE_CUDA_ERR_NOMEM;
-    size_t off = 0;
-    for (auto &j : jobs)
+    if (first_rc)
     {
-        if (!j.tokens.empty())
-            memcpy(toks + off, j.tokens.data(), j.tokens.size() * sizeof(u32));
-        off += j.tokens.size();
+        free(job.tokens);
+        free(job.merges);
+        return first_rc;
     }
     if (merges_out)
     {
-        const size_t nm = jobs[0].merges.size();
-        bpe_pair_t *mg = (bpe_pair_t *)malloc((nm ? nm : 1) * sizeof(bpe_pair_t));
-        if (!mg)
-        {
-            free(toks);
-            return BPE_CUDA_ERR_NOMEM;
-        }
-        if (nm)
-            memcpy(mg, jobs[0].merges.data(), nm * sizeof(bpe_pair_t));
-        *merges_out = mg;
-        *n_merges = nm;
+        *merges_out = job.merges;
+        *n_merges = job.n_merges;
     }
-    *tokens_out = toks;
-    *n_tokens = total;
+    else
+        free(job.merges);
+    *tokens_out = job.tokens;
+    *n_tokens = job.total_tokens;
     if (stats)
     {
         *stats = jobs[0].stats;
@@ -2395,7 +2682,7 @@ static int run_host(const uint8_t *bytes, size_t n_in, uint64_t max_merges, cons
             stats->ms_h2d = std::max(stats->ms_h2d, j.stats.ms_h2d);
             stats->ms_d2h = std::max(stats->ms_d2h, j.stats.ms_d2h);
         }
-        stats->n_tokens = total;
+        stats->n_tokens = job.total_tokens;
         stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
     return 0;
@@ -2404,15 +2691,39 @@ static int run_host(const uint8_t *bytes, size_t n_in, uint64_t max_merges, cons
 int bpe_cuda_train(const uint8_t *bytes, size_t n, uint64_t max_merges, int n_gpus, bpe_pair_t **merges_out, size_t *n_merges,
                    uint32_t **tokens_out, size_t *n_tokens, bpe_cuda_stats_t *stats)
 {
-    return run_host(bytes, n, max_merges, nullptr, 0, false, n_gpus, merges_out, n_merges, tokens_out, n_tokens, stats);
+    if (!bytes)
+    {
+        set_error("invalid argument");
+        return BPE_CUDA_ERR_ARG;
+    }
+    return run_host(bytes, n, nullptr, max_merges, nullptr, 0, false, n_gpus, merges_out, n_merges, tokens_out, n_tokens, stats);
 }
 
 int bpe_cuda_encode(const uint8_t *bytes, size_t n, const bpe_pair_t *merges, size_t n_merges, int n_gpus,
                     uint32_t **tokens_out, size_t *n_tokens, bpe_cuda_stats_t *stats)
 {
-    if (!merges && n_merges)
+    if ((!merges && n_merges) || !bytes)
         return BPE_CUDA_ERR_ARG;
-    return run_host(bytes, n, 0, merges, n_merges, true, n_gpus, nullptr, nullptr, tokens_out, n_tokens, stats);
+    return run_host(bytes, n, nullptr, 0, merges, n_merges, true, n_gpus, nullptr, nullptr, tokens_out, n_tokens, stats);
+}
+
+int bpe_cuda_train_file(const char *path, uint64_t max_merges, int n_gpus, bpe_pair_t **merges_out, size_t *n_merges,
+                        uint32_t **tokens_out, size_t *n_tokens, bpe_cuda_stats_t *stats)
+{
+    if (!path)
+    {
+        set_error("invalid argument");
+        return BPE_CUDA_ERR_ARG;
+    }
+    return run_host(nullptr, 0, path, max_merges, nullptr, 0, false, n_gpus, merges_out, n_merges, tokens_out, n_tokens, stats);
+}
+
+int bpe_cuda_encode_file(const char *path, const bpe_pair_t *merges, size_t n_merges, int n_gpus, uint32_t **tokens_out,
+                         size_t *n_tokens, bpe_cuda_stats_t *stats)
+{
+    if ((!merges && n_merges) || !path)
+        return BPE_CUDA_ERR_ARG;
+    return run_host(nullptr, 0, path, 0, merges, n_merges, true, n_gpus, nullptr, nullptr, tokens_out, n_tokens, stats);
 }
 
 } // extern "C"

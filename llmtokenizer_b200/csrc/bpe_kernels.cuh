@@ -404,34 +404,37 @@ __device__ inline void stream_ends(const DevState *st, u32 buf, u32 layout, u64 
 // K0 + K1: widen bytes to u32 tokens (bpe.c:580-584) and histogram all adjacent byte pairs into
 // a dense 256x256 table (every overlapping occurrence counts, bpe.c:460-471).  While all ids are
 // < 256 the dense table replaces the hash table.  16 bytes per thread: one 128-bit load, four
-// 128-bit stores.
-__global__ void __launch_bounds__(256) widen_count_kernel(const uint8_t *__restrict__ bytes, u64 n, u32 *__restrict__ tok,
+// 128-bit stores.  The launch covers the byte positions [lo, hi) (lo a multiple of 16) and counts the pair
+// that ENDS on each of them, so the corpus can be widened and counted chunk by chunk while later chunks are
+// still on their way from the host (file ingest): every pair is counted by exactly one launch, and only bytes in
+// front of `hi` are looked at.
+__global__ void __launch_bounds__(256) widen_count_kernel(const uint8_t *__restrict__ bytes, u64 lo, u64 hi, u32 *__restrict__ tok,
                                                           u32 *__restrict__ dense)
 {
     extern __shared__ __align__(16) u32 s_lo[]; // 128*128 privatised counts for pairs of 7-bit bytes (ASCII text)
     for (int i = threadIdx.x; i < 128 * 128; i += blockDim.x)
         s_lo[i] = 0;
     __syncthreads();
-    const u64 nvec = (n + 15) / 16;
-    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (u64)gridDim.x * blockDim.x)
+    const u64 v0 = lo / 16, nvec = (hi + 15) / 16;
+    for (u64 v = v0 + (u64)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (u64)gridDim.x * blockDim.x)
     {
         const u64 base = v * 16;
         const uint4 q = __ldg(reinterpret_cast<const uint4 *>(bytes) + v);
-        u32 c[17];
+        u32 c[17]; // c[k + 1] = byte at base + k, c[0] = the byte in front
         const u32 qq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int k = 0; k < 16; k++)
-            c[k] = (qq[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
-        c[16] = (base + 16 < n) ? (u32)bytes[base + 16] : 0u;
+            c[k + 1] = (qq[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
+        c[0] = base ? (u32)bytes[base - 1] : 0u;
         uint4 *o = reinterpret_cast<uint4 *>(tok + base);
-        o[0] = make_uint4(c[0], c[1], c[2], c[3]);
-        o[1] = make_uint4(c[4], c[5], c[6], c[7]);
-        o[2] = make_uint4(c[8], c[9], c[10], c[11]);
-        o[3] = make_uint4(c[12], c[13], c[14], c[15]);
+        o[0] = make_uint4(c[1], c[2], c[3], c[4]);
+        o[1] = make_uint4(c[5], c[6], c[7], c[8]);
+        o[2] = make_uint4(c[9], c[10], c[11], c[12]);
+        o[3] = make_uint4(c[13], c[14], c[15], c[16]);
 #pragma unroll
         for (int k = 0; k < 16; k++)
         {
-            if (base + k + 1 < n)
+            if (base + k < hi && base + k >= 1)
             {
                 const u32 x = c[k], y = c[k + 1];
                 if ((x | y) < 128u)

@@ -101,22 +101,28 @@ dyn_arr_t *compress_n(const char *path, uint32_t **encoding, size_t *len, size_t
 {
     if (!path || !encoding || !len) /* bpe.c:548-549 */
         return NULL;
-    char *buf = get_file(path);
-    if (!buf)
-        return NULL;
-    const size_t n = strlen(buf); /* bpe.c:555 */
-    if (n < 2)
     {
-        printf("Error: File contains less than 2 characters\n"); /* bpe.c:558-563 (stdout) */
-        free(buf);
-        return NULL;
+        /* the reference reports an unreadable file through perror (bpe.c:133-137) */
+        FILE *f = fopen(path, "r");
+        if (!f)
+        {
+            perror("fopen");
+            return NULL;
+        }
+        fclose(f);
     }
+    /* File ingest belongs to the engine (bpe.c:130-180 get_file, :555 strlen cut, :580-584 widen): the file is read in
+     * pinned 32 MB pieces, each copied to the GPU, widened and counted while the next one is being read. */
     bpe_pair_t *merges = NULL;
     uint32_t *tokens = NULL;
     size_t n_merges = 0, n_tokens = 0;
-    const int rc = bpe_cuda_train((const uint8_t *)buf, n, (uint64_t)max_merges, n_gpus < 1 ? 1 : n_gpus, &merges, &n_merges,
-                                  &tokens, &n_tokens, NULL);
-    free(buf);
+    const int rc = bpe_cuda_train_file(path, (uint64_t)max_merges, n_gpus < 1 ? 1 : n_gpus, &merges, &n_merges, &tokens, &n_tokens,
+                                       NULL);
+    if (rc == BPE_CUDA_ERR_SHORT)
+    {
+        printf("Error: File contains less than 2 characters\n"); /* bpe.c:558-563 (stdout) */
+        return NULL;
+    }
     if (rc != BPE_CUDA_OK)
     {
         fprintf(stderr, "compress: %s\n", bpe_cuda_last_error());
@@ -156,10 +162,7 @@ uint32_t *bpe_encode_file(const char *path, dyn_arr_t *pair_arr, size_t *len, in
 {
     if (!path || !pair_arr || !len || pair_arr->last_index < 255)
         return NULL;
-    char *buf = get_file(path);
-    if (!buf)
-        return NULL;
-    const size_t n = strlen(buf), n_merges = pair_arr->last_index - 255;
+    const size_t n_merges = pair_arr->last_index - 255;
     bpe_pair_t *merges = (bpe_pair_t *)malloc((n_merges ? n_merges : 1) * sizeof *merges);
     uint32_t *tokens = NULL;
     size_t n_tokens = 0;
@@ -173,9 +176,8 @@ uint32_t *bpe_encode_file(const char *path, dyn_arr_t *pair_arr, size_t *len, in
         merges[k].b = p.b;
     }
     if (rc == BPE_CUDA_OK)
-        rc = bpe_cuda_encode((const uint8_t *)buf, n, merges, n_merges, n_gpus < 1 ? 1 : n_gpus, &tokens, &n_tokens, NULL);
+        rc = bpe_cuda_encode_file(path, merges, n_merges, n_gpus < 1 ? 1 : n_gpus, &tokens, &n_tokens, NULL);
     free(merges);
-    free(buf);
     if (rc != BPE_CUDA_OK)
     {
         fprintf(stderr, "bpe_encode_file: %s\n", bpe_cuda_last_error());
@@ -186,16 +188,57 @@ uint32_t *bpe_encode_file(const char *path, dyn_arr_t *pair_arr, size_t *len, in
 }
 
 /* ---- output ---------------------------------------------------------------------------------- */
+/* bpe.c:182-196 prints one printf per token; a GB-scale encoding makes that the slowest part of main().  Same
+ * bytes on stdout, formatted into a 1 MB buffer and written in blocks. */
 void print_text(const uint32_t *text, int length) /* bpe.c:182-196 */
 {
+    enum
+    {
+        CAP = 1 << 20
+    };
+    char *buf = (char *)malloc(CAP + 16);
+    if (!buf)
+    {
+        for (int i = 0; i < length; i++)
+        {
+            if (text[i] < 32 || text[i] > 126)
+                printf("[%u]", text[i]);
+            else
+                printf("%c", (char)text[i]);
+        }
+        printf("\n");
+        return;
+    }
+    size_t w = 0;
     for (int i = 0; i < length; i++)
     {
-        if (text[i] < 32 || text[i] > 126)
-            printf("[%u]", text[i]);
+        const uint32_t t = text[i];
+        if (t >= 32 && t <= 126)
+            buf[w++] = (char)t;
         else
-            printf("%c", (char)text[i]);
+        {
+            char d[10];
+            int nd = 0;
+            uint32_t v = t;
+            do
+            {
+                d[nd++] = (char)('0' + v % 10);
+                v /= 10;
+            } while (v);
+            buf[w++] = '[';
+            while (nd)
+                buf[w++] = d[--nd];
+            buf[w++] = ']';
+        }
+        if (w >= CAP)
+        {
+            fwrite(buf, 1, w, stdout);
+            w = 0;
+        }
     }
-    printf("\n");
+    buf[w++] = '\n';
+    fwrite(buf, 1, w, stdout);
+    free(buf);
 }
 
 /* ---- decode (bpe.c:12-128, 341-394): ids -> bytes through the vocabulary --------------------- */
@@ -219,29 +262,66 @@ static size_t *expansion_lengths(dyn_arr_t *pair_arr)
     return L;
 }
 
-/* write the expansion of id to out (iteratively: an explicit stack instead of the reference's recursion) */
-static char *expand_into(uint32_t id, dyn_arr_t *pair_arr, char *out)
+/* Write the expansion of id to out[0 .. cap) (iteratively: an explicit, growing stack instead of the reference's
+ * recursion).  The vocabulary is not trusted: an id may only refer to EARLIER ids (a pairs file can say anything), and
+ * nothing is written beyond the length expansion_lengths() computed.  Returns the end of the output, NULL on a bad
+ * vocabulary or when memory runs out. */
+static char *expand_into(uint32_t id, dyn_arr_t *pair_arr, char *out, size_t cap)
 {
-    uint32_t stack[128];
-    int sp = 0;
+    size_t scap = 64, sp = 0;
+    uint32_t *stack = (uint32_t *)malloc(scap * sizeof *stack);
+    char *const end = out + cap;
+    if (!stack)
+        return NULL;
     stack[sp++] = id;
     while (sp)
     {
         const uint32_t t = stack[--sp];
         if (t < 256)
         {
+            if (out == end)
+                goto bad;
             *out++ = (char)t;
             continue;
         }
         pair_t p;
-        if (!dyn_arr_get(pair_arr, t, &p) || sp + 2 > 128)
-            return NULL;
-        /* right first so the left part is emitted first; depth is bounded by the chain of left parts,
-         * which a 128-deep stack covers for any realistic vocabulary (falls back to NULL otherwise) */
-        stack[sp++] = p.b;
+        if (!dyn_arr_get(pair_arr, t, &p) || p.a >= t || p.b >= t)
+            goto bad;
+        if (sp + 2 > scap)
+        {
+            uint32_t *ns = (uint32_t *)realloc(stack, 2 * scap * sizeof *stack);
+            if (!ns)
+                goto bad;
+            stack = ns;
+            scap *= 2;
+        }
+        stack[sp++] = p.b; /* right first so the left part is emitted first */
         stack[sp++] = p.a;
     }
+    free(stack);
     return out;
+bad:
+    free(stack);
+    return NULL;
+}
+
+/* resolve_pair() with the lengths already known (render_pairs computes them once, not once per id) */
+static char *resolve_with_lengths(uint32_t pair_index, dyn_arr_t *pair_arr, const size_t *L)
+{
+    const size_t n = L[pair_index];
+    if (n == 0) /* undefined id, or one that refers to itself / a later id */
+        return NULL;
+    char *s = (char *)malloc(n + 1);
+    if (!s)
+        return NULL;
+    char *end = expand_into(pair_index, pair_arr, s, n);
+    if (!end)
+    {
+        free(s);
+        return NULL;
+    }
+    *end = '\0';
+    return s;
 }
 
 char *resolve_pair(uint32_t pair_index, dyn_arr_t *pair_arr, hash_table_t *memoization_table) /* bpe.c:23-92 */
@@ -259,18 +339,11 @@ char *resolve_pair(uint32_t pair_index, dyn_arr_t *pair_arr, hash_table_t *memoi
     size_t *L = expansion_lengths(pair_arr);
     if (!L)
         return NULL;
+    char *s = resolve_with_lengths(pair_index, pair_arr, L);
     const size_t n = L[pair_index];
     free(L);
-    char *s = (char *)malloc(n + 1);
     if (!s)
         return NULL;
-    char *end = expand_into(pair_index, pair_arr, s);
-    if (!end)
-    {
-        free(s);
-        return NULL;
-    }
-    *end = '\0';
     if (memoization_table)
     {
         char *keep = (char *)malloc(n + 1);
@@ -321,14 +394,18 @@ void render_pairs(dyn_arr_t *pair_arr) /* bpe.c:94-128 */
 {
     if (!pair_arr)
         return;
+    size_t *L = expansion_lengths(pair_arr);
+    if (!L)
+        return;
     for (size_t index = 256; index <= pair_arr->last_index; index++)
     {
-        char *str = resolve_pair((uint32_t)index, pair_arr, NULL);
+        char *str = resolve_with_lengths((uint32_t)index, pair_arr, L);
         if (!str)
-            return;
+            break;
         fprintf(stdout, "%zu => %s\n", index, str);
         free(str);
     }
+    free(L);
 }
 
 /* ---- merge-table file: little-endian {u32 a; u32 b} records from id 256, no header (bpe.c:243-339) */
@@ -372,11 +449,23 @@ dyn_arr_t *read_pairs(const char *path)
     pair_t p;
     size_t index = 256;
     while (arr && fread(&p, sizeof p, 1, f) == 1)
+    {
+        /* a merge may only combine ids that exist already (bpe.c:752-758 creates them in order); a file that says
+         * otherwise would send every expansion into a cycle */
+        if (p.a >= index || p.b >= index)
+        {
+            fprintf(stderr, "read_pairs: record %zu refers to id %u, which does not exist yet\n", index - 256,
+                    p.a >= index ? p.a : p.b);
+            dyn_arr_free(arr);
+            arr = NULL;
+            break;
+        }
         if (!dyn_arr_set(arr, index++, &p))
         {
             dyn_arr_free(arr);
             arr = NULL;
         }
+    }
     fclose(f);
     return arr;
 }

@@ -93,6 +93,46 @@ def test_host_side_decode_and_pair_file(lib, tmp_path):
     lib.dyn_arr_free(arr)
 
 
+def test_hostile_vocabularies_are_rejected(lib, tmp_path):
+    """A pairs file is input: an id that refers to itself or to a later id (300 = (65, 300)) must not send the
+    expansion into a cycle or past its buffer (resolve_pair / render_pairs, bpe.c:23-128), and read_pairs refuses it."""
+    lib.resolve_pair.restype = C.c_void_p
+    lib.resolve_pair.argtypes = [C.c_uint32, C.POINTER(DynArr), C.c_void_p]
+    arr = vocabulary(lib, [(97, 98), (65, 257), (258, 97), (256, 256)])   # 257 refers to itself, 258 to a later id
+    assert not lib.resolve_pair(257, arr, None) and not lib.resolve_pair(258, arr, None)
+    s = lib.resolve_pair(259, arr, None)                                   # 259 = (256, 256) is fine
+    assert s and C.string_at(s) == b"abab"
+    C.CDLL(None).free(C.c_void_p(s))
+    lib.dyn_arr_free(arr)
+    bad = tmp_path / "bad.bin"
+    np.array([[97, 98], [65, 257]], dtype="<u4").tofile(bad)
+    assert not lib.read_pairs(str(bad).encode())
+    # left-deep chains far beyond the old 128-entry stack: id 256+k = (256+k-1, 'x')
+    deep = [(97, 98)] + [(256 + k, 120) for k in range(2000)]
+    arr = vocabulary(lib, deep)
+    s = lib.resolve_pair(256 + 2000, arr, None)
+    assert s and C.string_at(s) == b"ab" + b"x" * 2000
+    C.CDLL(None).free(C.c_void_p(s))
+    lib.dyn_arr_free(arr)
+
+
+def test_print_text_matches_the_reference_format(lib, tmp_path):
+    """bpe.c:182-196: 32..126 as the character, everything else as [id]; one block write per MB instead of one printf
+    per token, same bytes."""
+    ids = np.concatenate([np.arange(0, 300, dtype=np.uint32), np.random.default_rng(1).integers(0, 70000, 300_000).astype(np.uint32)])
+    want = "".join(chr(int(t)) if 32 <= t <= 126 else f"[{int(t)}]" for t in ids) + "\n"
+    src = tmp_path / "p.c"
+    src.write_text('#include "bpe/inc/bpe.h"\n#include <stdio.h>\nint main(int c, char **v){FILE *f=fopen(v[1],"rb");fseek(f,0,SEEK_END);'
+                   'long n=ftell(f)/4;rewind(f);uint32_t *t=malloc(n*4+4);if(fread(t,4,n,f)!=(size_t)n)return 1;print_text(t,(int)n);return 0;}\n')
+    exe = tmp_path / "p"
+    subprocess.check_call(["gcc", "-O1", "-o", str(exe), str(src), "-I", DROPIN, "-L", DROPIN, "-lbpe", f"-Wl,-rpath,{DROPIN}",
+                           "-L", os.path.join(ROOT, "llmtokenizer_b200"), "-lbpe_cuda", f"-Wl,-rpath,{os.path.join(ROOT, 'llmtokenizer_b200')}"])
+    data = tmp_path / "ids.bin"
+    ids.astype("<u4").tofile(data)
+    out = subprocess.run([str(exe), str(data)], capture_output=True, check=True).stdout
+    assert out.decode("latin-1") == want
+
+
 @pytest.mark.gpu
 def test_decompress_inverts_compress(lib):
     # decompress() (bpe.c:341-394) runs the GPU decode: decompress(compress(x)) == x

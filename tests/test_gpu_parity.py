@@ -354,6 +354,39 @@ def test_more_gpus_than_devices_is_an_error(engine):
     assert e.value.rc in (-4, -1)
 
 
+def test_file_ingest_equals_training_from_memory(engine, tmp_path):
+    """bpe_cuda_train_file (bpe.c:130-180 get_file + :555 strlen cut + :580-584 widen in front of the path): the file is
+    read in 32 MB pinned pieces that are copied, widened and counted while the next piece is read.  Same merges and ids
+    as the in-memory entry point: pairs that straddle two pieces, a 0x00 in the third piece, files shorter than a piece,
+    and the same through the drop-in's compress() a reference caller uses."""
+    data = corpus(0, 75_000_000, 41)                 # three pieces: 32 + 32 + 11 MB
+    data[70_000_001] = 0                             # strlen cut inside the third piece
+    data[33_554_431], data[33_554_432] = 113, 117    # a pair across the first piece boundary
+    p = tmp_path / "corpus.bin"
+    data.tofile(p)
+    m0, t0, _ = engine.train(data, max_merges=300)
+    m1, t1, st = engine.train_file(str(p), max_merges=300)
+    assert st["n_input"] == 70_000_001 and np.array_equal(m0, m1) and np.array_equal(t0, t1)
+    ids0, _ = engine.encode(data, m0)
+    ids1, _ = engine.encode_file(str(p), m0)
+    assert np.array_equal(ids0, ids1) and np.array_equal(ids0, t0)
+    small = tmp_path / "small.bin"
+    data[:1_000_003].tofile(small)
+    ms, ts, _ = engine.train(data[:1_000_003], max_merges=50)
+    mf, tf, _ = engine.train_file(str(small), max_merges=50)
+    assert np.array_equal(ms, mf) and np.array_equal(ts, tf)
+    pair_arr, ids = engine.compress(str(p), max_merges=300)
+    assert np.array_equal(pair_arr[256:], m0) and np.array_equal(ids, t0)
+    if _device_count() >= 2:                          # every rank reads its own byte range; the NUL is rank 1's
+        m2, t2, st2 = engine.train_file(str(p), max_merges=300, n_gpus=2)
+        assert np.array_equal(m0, m2) and np.array_equal(t0, t2)
+        data[20_000_000] = 0                          # ... and now rank 0's: rank 1's part is dropped
+        data.tofile(p)
+        m3, t3, _ = engine.train(data, max_merges=100)
+        m4, t4, _ = engine.train_file(str(p), max_merges=100, n_gpus=2)
+        assert np.array_equal(m3, m4) and np.array_equal(t3, t4)
+
+
 def _full_golden(name):
     import json
     import os
