@@ -580,6 +580,7 @@ def bench_engine(args, w, rank, world, local):
                           "what": "compress_n(path, &ids, &len, merges, 1) of the drop-in libbpe.so on a file: file read, "
                                   "NUL cut, H2D, training, D2H, dyn_arr vocabulary (bpe.c:541-811)"}
             e2e_paths = {"bpe_cuda_train": {"value": len(m1) / one_call, "unit": "merges/s", "seconds": one_call,
+                                            "inside_ms": {k: round(s1[k], 1) for k in ("ms_h2d", "ms_device", "ms_d2h", "ms_total")},
                                             "what": "one call from pageable host memory: context + table creation, H2D, training, "
                                                     "D2H into malloc'd buffers"},
                          "dropin_compress": dropin}

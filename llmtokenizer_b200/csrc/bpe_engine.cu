@@ -2120,6 +2120,32 @@ static int download_staged(bpe_cuda_ctx *c, void *dst, const void *src_dev, size
     int rc;
     if ((rc = ensure_staging(c)))
         return rc;
+    // The destination is fresh malloc'd memory: its pages are faulted in on first touch, which a single copying
+    // thread does at ~2 GB/s (measured: 0.55 s for the 1.17 GB of ids of the 1 GB corpus).  Helper threads touch the
+    // pages ahead of the copy.
+    std::vector<std::thread> toucher;
+    if (bytes >= (64u << 20))
+    {
+        const int T = 3;
+        for (int t = 0; t < T; t++)
+            toucher.emplace_back([=] {
+                // (an atomic add of zero: faults the page in for writing without changing what the copy may already
+                // have put there)
+                char *p = (char *)dst;
+                const size_t lo = bytes / T * (size_t)t, hi = (t == T - 1) ? bytes : bytes / T * (size_t)(t + 1);
+                for (size_t o = (lo + 4095) & ~(size_t)4095; o < hi; o += 4096)
+                    __atomic_fetch_add(p + o, (char)0, __ATOMIC_RELAXED);
+            });
+    }
+    struct Joiner
+    {
+        std::vector<std::thread> &v;
+        ~Joiner()
+        {
+            for (auto &t : v)
+                t.join();
+        }
+    } joiner{toucher};
     size_t issued = 0, copied = 0, len[2] = {0, 0};
     int head = 0, next = 0, inflight = 0; // head: the buffer that holds the oldest piece still on its way
     while (copied < bytes)
