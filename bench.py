@@ -523,7 +523,7 @@ def bench_engine(args, w, rank, world, local):
                 ctx.set_option("batch_max", 1)             # one merge per pass: the sequential order by construction
                 ctx.train(M)
                 m_1, t_1 = ctx.download()
-                ctx.set_option("batch_max", 8)
+                ctx.set_option("batch_max", 15)             # (clamped to the build's BATCH_MAX)
                 checks["batched_passes_equal_one_merge_per_pass"] = bool(sha(m_b) == sha(m_1) and sha(t_b) == sha(t_1))
     else:
         run()

@@ -25,7 +25,7 @@ constexpr u64 NO_SLOT = ~0ull;
 
 constexpr int MAX_RANKS = 8;
 #ifndef BPE_BATCH_MAX
-#define BPE_BATCH_MAX 8
+#define BPE_BATCH_MAX 12
 #endif
 constexpr int BATCH_MAX = BPE_BATCH_MAX; // merges per pass (at most 15: a nibble holds 1 + the pair index)
 // batched passes look tokens up in a byte table indexed by (token mod CLS_SIZE): the tokens of a batch must
@@ -599,9 +599,8 @@ __device__ inline void xchg_signal(DevState *st, u32 seq, u32 count)
         if (p != st->rank)
             st->x.peer[p][XCHG_COUNTS + (seq & 1u) * MAX_RANKS + st->rank] = count;
     __threadfence_system();
-    for (u32 p = 0; p < st->world; p++)
-        if (p != st->rank)
-            st_release_sys(st->x.peer[p] + XCHG_FLAGS + st->rank, seq);
+    for (u32 p = 0; p < st->world; p++) // (my own inbox too: this rank's blocks wait for "my list is complete" there)
+        st_release_sys(st->x.peer[p] + XCHG_FLAGS + st->rank, seq);
 }
 // one thread: wait until `sender` has raised its flag for exchange `seq` in my inbox.  Peers run the same launch
 // sequence on their own GPUs; a flag that does not arrive within x_timeout_ns (20 s) means a rank died or fell out of step:
@@ -1761,6 +1760,10 @@ __device__ __noinline__ void add_peer_lists(DevState *st, int32_t *delta, u32 gt
     __shared__ u32 s_cnt;
     const u64 xcap = st->x.xcap;
     const u32 me = st->rank, P = st->world, par = seq & 1u;
+    // Nothing may be added to the vectors while a block of THIS rank is still reading them for its pushes
+    // (push_deltas): my own flag goes up when the last of them is done.
+    if (threadIdx.x == 0)
+        xchg_wait(st, me, seq);
     for (u32 k = 1; k < P; k++)
     {
         const u32 sender = (me + k) % P;

@@ -7,7 +7,7 @@ key = sys.argv[1]; P = int(sys.argv[2]); reps = int(sys.argv[3])
 data, cap = pc.train_input(key)
 exp = pc.expected_train(key)
 om = exp["merges"]
-for envs in ({}, {"BPE_CUDA_SPECULATE": "0"}):
+for envs in ({},):
     for k in ("BPE_CUDA_PDL", "BPE_CUDA_SPECULATE", "BPE_CUDA_BATCH_MAX"):
         os.environ.pop(k, None)
     os.environ.update(envs)
