@@ -223,13 +223,13 @@ def test_batched_passes_beyond_the_class_table(engine, oracle):
     data, cap = pc.train_input(key)
     exp = pc.expected_train(key, oracle)
     res = []
-    for bm in (8, 1):
+    for bm in (12, 1):
         ctx = engine.Context(0)
         ctx.set_option("batch_max", bm)
         ctx.upload(data)
         st = ctx.train(cap)
         m, t = ctx.download()
-        if bm == 8:
+        if bm == 12:
             assert st["batch_merges"] > 0 and ctx.decode(m, download=False) == data.size and ctx.decode_mismatches() == 0
         ctx.close()
         check_result(exp, m, t, st, 1, f"{key} batch_max {bm}")
