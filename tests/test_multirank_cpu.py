@@ -28,7 +28,20 @@ if rank == 0:
 dist.broadcast(idt, 0)
 assert idt.tolist() == list(range(128))
 assert bench.max_over_ranks(1.0 + rank, world) == 2.0
+assert bench.sum_over_ranks(1.0 + rank, world) == 3.0
 bench.barrier(world)
+# the digest of the ranks' id arrays in rank order (how bench.py checks sharded results against the oracle's digest)
+import hashlib
+parts = [np.arange(5, dtype=np.uint32), np.arange(100, 107, dtype=np.uint32)]
+got = bench.sha_over_ranks(parts[rank], rank, world)
+if rank == 0:
+    assert got == hashlib.sha256(np.concatenate(parts).astype("<u4").tobytes()).hexdigest()
+# every rank generates only its own shard of a chunked corpus (configs 4 and 5): together they are the corpus
+w = dict(kind=1, size=10_500, seed=3, chunk=1000)
+whole = np.empty(w["size"], dtype=np.uint8); bench.fill_corpus(w, whole, 0, w["size"])
+lo, hi = w["size"] * rank // world, w["size"] * (rank + 1) // world
+mine = np.empty(hi - lo, dtype=np.uint8); bench.fill_corpus(w, mine, lo, hi)
+assert np.array_equal(mine, whole[lo:hi]) and whole.min() > 0
 # shard bounds + edge records: each rank rewrites its shard with the tokens it gets from the other rank's record
 oracle = oracle_api.load()
 rng = np.random.default_rng(5)
