@@ -25,6 +25,7 @@
  */
 #include "bpe_oracle.h"
 
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -34,6 +35,60 @@
 #define BO_THREAD_BUCKETS 256u                   /* bpe.c:610 */
 #define BO_MERGED_BUCKETS 65536u                 /* bpe.c:611 */
 #define BO_SENT 0xFFFFFFFFu                      /* "no token here" in halo windows */
+
+/* ------------------------------------------------------------------------------------------ */
+/* Optional helper threads for the FAST modes' two whole-array loops (argmax scan of the count
+ * map, rewrite + delta emission).  They only split the same loops over index ranges and combine
+ * the partial results in range order, so every result is the one the sequential loops give
+ * (tests/test_oracle.py checks that); default: off.  Used offline for the full-size fixtures
+ * (tools/make_full_golden.py), where a 1 GB corpus costs ~1 s per merge on one core. */
+#define BO_MAX_WORKERS 64
+static int g_workers = 1;
+static size_t g_workers_min_n = (size_t)1 << 22;
+
+void bo_set_workers(int workers, size_t min_tokens)
+{
+    g_workers = workers < 1 ? 1 : (workers > BO_MAX_WORKERS ? BO_MAX_WORKERS : workers);
+    g_workers_min_n = min_tokens;
+}
+
+typedef struct
+{
+    void (*fn)(void *ctx, int w, int nw);
+    void *ctx;
+    int w, nw;
+} par_job_t;
+
+static void *par_tramp(void *p)
+{
+    par_job_t *j = (par_job_t *)p;
+    j->fn(j->ctx, j->w, j->nw);
+    return NULL;
+}
+
+/* fork-join: fn(ctx, w, nw) for w = 0..nw-1, worker 0 on the calling thread */
+static void par_run(void (*fn)(void *, int, int), void *ctx, int nw)
+{
+    pthread_t th[BO_MAX_WORKERS];
+    par_job_t job[BO_MAX_WORKERS];
+    int started[BO_MAX_WORKERS];
+    for (int w = 1; w < nw; w++)
+    {
+        job[w].fn = fn;
+        job[w].ctx = ctx;
+        job[w].w = w;
+        job[w].nw = nw;
+        started[w] = (pthread_create(&th[w], NULL, par_tramp, &job[w]) == 0);
+    }
+    fn(ctx, 0, nw);
+    for (int w = 1; w < nw; w++)
+    {
+        if (started[w])
+            pthread_join(th[w], NULL);
+        else
+            fn(ctx, w, nw); /* no thread to be had: do the share here */
+    }
+}
 
 /* ------------------------------------------------------------------------------------------ */
 /* hash_table.c:8-53 specialised to the 8-byte key {u32 a; u32 b} (two blocks, no tail)        */
@@ -208,13 +263,26 @@ typedef struct
     uint32_t *hsh;
     uint64_t cap, used;
     uint64_t distinct; /* D: entries with cnt > 0 */
+    /* argmax shortcut: the slots whose count has reached cand_T since the list was made (0: no
+     * list).  Only an increment can carry a count over cand_T, and pmap_add offers those, so while
+     * the largest count in the list is >= cand_T the list holds every maximal entry. */
+    uint64_t *cand, *inlist;
+    uint64_t cand_n, cand_cap;
+    uint32_t cand_T;
 } pmap_t;
+
+static uint32_t g_cand_floor = 64; /* a list is only made while the maximum count is at least this; 0: never */
+
+void bo_set_candidate_floor(uint32_t min_count) { g_cand_floor = min_count; }
 
 static int pmap_init(pmap_t *m, uint64_t cap)
 {
     m->cap = cap;
     m->used = 0;
     m->distinct = 0;
+    m->cand = m->inlist = NULL;
+    m->cand_n = m->cand_cap = 0;
+    m->cand_T = 0;
     m->key = (uint64_t *)malloc(cap * sizeof(uint64_t));
     m->cnt = (uint32_t *)calloc(cap, sizeof(uint32_t));
     m->hsh = (uint32_t *)malloc(cap * sizeof(uint32_t));
@@ -230,7 +298,45 @@ static void pmap_release(pmap_t *m)
     free(m->key);
     free(m->cnt);
     free(m->hsh);
+    free(m->cand);
+    free(m->inlist);
     memset(m, 0, sizeof *m);
+}
+
+static int cand_push(pmap_t *m, uint64_t s)
+{
+    if (m->inlist[s >> 6] >> (s & 63) & 1)
+        return 0;
+    m->inlist[s >> 6] |= 1ull << (s & 63);
+    if (m->cand_n == m->cand_cap)
+    {
+        uint64_t nc = m->cand_cap ? m->cand_cap * 2 : 4096;
+        uint64_t *c2 = (uint64_t *)realloc(m->cand, nc * sizeof(uint64_t));
+        if (!c2)
+            return -1;
+        m->cand = c2;
+        m->cand_cap = nc;
+    }
+    m->cand[m->cand_n++] = s;
+    return 0;
+}
+
+/* (re)build the list for threshold T from the whole map */
+static int cand_build(pmap_t *m, uint32_t T)
+{
+    if (!m->inlist)
+        m->inlist = (uint64_t *)malloc((m->cap / 64 + 1) * sizeof(uint64_t));
+    if (!m->inlist)
+        return -1;
+    memset(m->inlist, 0, (m->cap / 64 + 1) * sizeof(uint64_t));
+    m->cand_n = 0;
+    m->cand_T = 0;
+    for (uint64_t s = 0; s < m->cap; s++)
+        if (m->key[s] != PM_EMPTY && m->cnt[s] >= T)
+            if (cand_push(m, s))
+                return -1;
+    m->cand_T = T;
+    return 0;
 }
 
 static int64_t pmap_find(const pmap_t *m, uint64_t key, uint32_t h)
@@ -305,6 +411,8 @@ static int pmap_add(pmap_t *m, uint32_t a, uint32_t b, int64_t d)
     uint32_t before = m->cnt[s];
     uint32_t after = (uint32_t)((int64_t)before + d);
     m->cnt[s] = after;
+    if (m->cand_T && before < m->cand_T && after >= m->cand_T && cand_push(m, (uint64_t)s))
+        return -1;
     if (!before && after)
         m->distinct++;
     if (before && !after)
@@ -813,6 +921,146 @@ static size_t rewrite_with_deltas(const uint32_t *in, size_t n, uint32_t a, uint
     return m;
 }
 
+/* ---- the same two loops split over helper threads (bo_set_workers) ---------------------- */
+/* first position a worker whose share starts at `bound` has to look at: `bound` itself, or the
+ * one behind it when `bound` is the second token of a replacement that starts at bound - 1
+ * (a != b: occurrences cannot overlap, so every occurrence is a replacement; a == b: replacements
+ * pair up from the start of the run, bpe.c:760-772 scanning left to right) */
+static size_t share_start(const uint32_t *in, size_t n, size_t bound, uint32_t a, uint32_t b)
+{
+    if (bound == 0 || bound >= n)
+        return bound > n ? n : bound;
+    if (a != b)
+        return (in[bound - 1] == a && in[bound] == b) ? bound + 1 : bound;
+    if (in[bound] != a)
+        return bound;
+    size_t r = bound;
+    while (r > 0 && in[r - 1] == a)
+        r--;
+    return ((bound - r) & 1) ? bound + 1 : bound;
+}
+
+typedef struct
+{
+    const uint32_t *in;
+    size_t n;
+    uint32_t a, b, z;
+    uint32_t *out;
+    int32_t *delta0, *delta_rest; /* worker 0 / workers 1.. (delta_len each) */
+    size_t delta_len;
+    size_t start[BO_MAX_WORKERS + 1], cnt[BO_MAX_WORKERS], off[BO_MAX_WORKERS];
+    int write;
+} prw_t;
+
+static void prw_worker(void *ctx, int w, int nw)
+{
+    prw_t *c = (prw_t *)ctx;
+    (void)nw;
+    const uint32_t *in = c->in;
+    const size_t n = c->n, end = c->start[w + 1];
+    const uint32_t a = c->a, b = c->b, z = c->z;
+    if (!c->write)
+    {
+        size_t m = 0;
+        for (size_t i = c->start[w]; i < end; i++, m++)
+            if (i + 1 < n && in[i] == a && in[i + 1] == b)
+                i++;
+        c->cnt[w] = m;
+        return;
+    }
+    uint32_t *out = c->out + c->off[w];
+    int32_t *delta = w ? c->delta_rest + (size_t)(w - 1) * c->delta_len : c->delta0;
+    size_t m = 0;
+    for (size_t i = c->start[w]; i < end; i++)
+    {
+        if (i + 1 < n && in[i] == a && in[i + 1] == b)
+        {
+            match_deltas(in + i, a, b, z, delta);
+            out[m++] = z;
+            i++;
+        }
+        else
+            out[m++] = in[i];
+    }
+}
+
+static size_t rewrite_with_deltas_par(const uint32_t *in, size_t n, uint32_t a, uint32_t b, uint32_t z, uint32_t *out,
+                                      int32_t *delta0, int32_t *delta_rest, size_t delta_len, int nw)
+{
+    prw_t c;
+    memset(&c, 0, sizeof c);
+    c.in = in;
+    c.n = n;
+    c.a = a;
+    c.b = b;
+    c.z = z;
+    c.out = out;
+    c.delta0 = delta0;
+    c.delta_rest = delta_rest;
+    c.delta_len = delta_len;
+    for (int w = 0; w < nw; w++)
+        c.start[w] = share_start(in, n, (size_t)((unsigned __int128)n * (unsigned)w / (unsigned)nw), a, b);
+    c.start[nw] = n;
+    c.write = 0;
+    par_run(prw_worker, &c, nw);
+    size_t total = 0;
+    for (int w = 0; w < nw; w++)
+    {
+        c.off[w] = total;
+        total += c.cnt[w];
+    }
+    c.write = 1;
+    par_run(prw_worker, &c, nw);
+    const size_t used = ((size_t)z + 1) * 4;
+    for (int w = 1; w < nw; w++)
+    {
+        int32_t *d = delta_rest + (size_t)(w - 1) * delta_len;
+        for (size_t k = 0; k < used; k++)
+            if (d[k])
+            {
+                delta0[k] += d[k];
+                d[k] = 0;
+            }
+    }
+    return total;
+}
+
+typedef struct
+{
+    const pmap_t *pm;
+    uint64_t bm;
+    uint32_t freq[BO_MAX_WORKERS];
+    uint64_t bucket[BO_MAX_WORKERS], mult[BO_MAX_WORKERS], key[BO_MAX_WORKERS];
+} pam_t;
+
+static void pam_worker(void *ctx, int w, int nw)
+{
+    pam_t *c = (pam_t *)ctx;
+    const pmap_t *pm = c->pm;
+    const uint64_t lo = (uint64_t)((unsigned __int128)pm->cap * (unsigned)w / (unsigned)nw);
+    const uint64_t hi = (uint64_t)((unsigned __int128)pm->cap * (unsigned)(w + 1) / (unsigned)nw);
+    uint32_t bf = 0;
+    uint64_t bb = 0, mult = 0, key = 0;
+    for (uint64_t s = lo; s < hi; s++)
+        if (pm->key[s] != PM_EMPTY && pm->cnt[s])
+        {
+            uint64_t bk = (uint64_t)pm->hsh[s] % c->bm;
+            if (pm->cnt[s] > bf || (pm->cnt[s] == bf && bk < bb))
+            {
+                bf = pm->cnt[s];
+                bb = bk;
+                key = pm->key[s];
+                mult = 1;
+            }
+            else if (pm->cnt[s] == bf && bk == bb)
+                mult++;
+        }
+    c->freq[w] = bf;
+    c->bucket[w] = bb;
+    c->mult[w] = mult;
+    c->key[w] = key;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 int bo_train(const uint8_t *bytes, size_t n_in, uint64_t max_merges, int mode, bo_pair_t **merges_out,
              size_t *n_merges_out, uint32_t **tokens_out, size_t *n_tokens_out, bo_stats_t *stats)
@@ -830,8 +1078,8 @@ int bo_train(const uint8_t *bytes, size_t n_in, uint64_t max_merges, int mode, b
     uint32_t *buf1 = (uint32_t *)malloc((n + 2 * pad) * sizeof(uint32_t));
     size_t mcap = 1024, nm = 0;
     bo_pair_t *merges = (bo_pair_t *)malloc(mcap * sizeof(bo_pair_t));
-    int32_t *delta = NULL;
-    size_t delta_cap = 0;
+    int32_t *delta = NULL, *pdelta = NULL;
+    size_t delta_cap = 0, pdelta_len = 0;
     emu_t emu;
     pmap_t pm;
     memset(&pm, 0, sizeof pm);
@@ -883,6 +1131,61 @@ int bo_train(const uint8_t *bytes, size_t n_in, uint64_t max_merges, int mode, b
                 break;
             const uint64_t bm = bo_merged_buckets(D);
             uint64_t best_bucket = 0, mult = 0;
+            const int nw = (g_workers > 1 && n >= g_workers_min_n && n >= 8u * (size_t)g_workers) ? g_workers : 1;
+            int from_list = 0;
+            if (pm.cand_T)
+            {
+                for (uint64_t k = 0; k < pm.cand_n; k++)
+                {
+                    const uint64_t s = pm.cand[k];
+                    if (!pm.cnt[s])
+                        continue;
+                    uint64_t bk = (uint64_t)pm.hsh[s] % bm;
+                    if (pm.cnt[s] > best_freq || (pm.cnt[s] == best_freq && bk < best_bucket))
+                    {
+                        best_freq = pm.cnt[s];
+                        best_bucket = bk;
+                        best.a = (uint32_t)(pm.key[s] & 0xFFFFFFFFu);
+                        best.b = (uint32_t)(pm.key[s] >> 32);
+                        mult = 1;
+                    }
+                    else if (pm.cnt[s] == best_freq && bk == best_bucket)
+                        mult++;
+                }
+                if (best_freq >= pm.cand_T)
+                    from_list = 1; /* every maximal entry is in the list */
+                else
+                {
+                    pm.cand_T = 0; /* the maximum may sit below the threshold: look at the whole map */
+                    best_freq = 0;
+                    best_bucket = mult = 0;
+                }
+            }
+            if (from_list)
+                ;
+            else if (nw > 1)
+            {
+                pam_t pa;
+                pa.pm = &pm;
+                pa.bm = bm;
+                par_run(pam_worker, &pa, nw);
+                for (int w = 0; w < nw; w++) /* shares in slot order: the first maximum stays the first */
+                {
+                    if (!pa.freq[w])
+                        continue;
+                    if (pa.freq[w] > best_freq || (pa.freq[w] == best_freq && pa.bucket[w] < best_bucket))
+                    {
+                        best_freq = pa.freq[w];
+                        best_bucket = pa.bucket[w];
+                        best.a = (uint32_t)(pa.key[w] & 0xFFFFFFFFu);
+                        best.b = (uint32_t)(pa.key[w] >> 32);
+                        mult = pa.mult[w];
+                    }
+                    else if (pa.freq[w] == best_freq && pa.bucket[w] == best_bucket)
+                        mult += pa.mult[w];
+                }
+            }
+            else
             for (uint64_t s = 0; s < pm.cap; s++)
                 if (pm.key[s] != PM_EMPTY && pm.cnt[s])
                 {
@@ -898,6 +1201,9 @@ int bo_train(const uint8_t *bytes, size_t n_in, uint64_t max_merges, int mode, b
                     else if (pm.cnt[s] == best_freq && bk == best_bucket)
                         mult++;
                 }
+            if (!from_list && g_cand_floor && best_freq >= g_cand_floor)
+                if (cand_build(&pm, best_freq / 2 ? best_freq / 2 : 1))
+                    goto done;
             int on_threshold = 0;
             for (uint64_t b = BO_MERGED_BUCKETS; resize_threshold(b) <= D; b *= 2)
                 if (resize_threshold(b) == D)
@@ -971,7 +1277,21 @@ int bo_train(const uint8_t *bytes, size_t n_in, uint64_t max_merges, int mode, b
             }
             for (size_t i = 0; i < pad; i++)
                 text[n + i] = BO_SENT;
-            new_n = rewrite_with_deltas(text, n, best.a, best.b, next_symbol, temp, delta);
+            const int nw = (g_workers > 1 && n >= g_workers_min_n && n >= 8u * (size_t)g_workers) ? g_workers : 1;
+            if (nw > 1)
+            {
+                if (pdelta_len != delta_cap) /* the helpers' vectors: all zero between merges */
+                {
+                    free(pdelta);
+                    pdelta = (int32_t *)calloc((size_t)(BO_MAX_WORKERS - 1) * delta_cap, sizeof(int32_t));
+                    if (!pdelta)
+                        goto done;
+                    pdelta_len = delta_cap;
+                }
+                new_n = rewrite_with_deltas_par(text, n, best.a, best.b, next_symbol, temp, delta, pdelta, pdelta_len, nw);
+            }
+            else
+                new_n = rewrite_with_deltas(text, n, best.a, best.b, next_symbol, temp, delta);
             if (apply_deltas(&pm, best.a, best.b, next_symbol, delta))
                 goto done;
         }
@@ -1007,6 +1327,7 @@ done:
     free(buf1);
     free(merges);
     free(delta);
+    free(pdelta);
     emu_release(&emu);
     if (pm.key)
         pmap_release(&pm);

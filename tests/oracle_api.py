@@ -41,6 +41,15 @@ class Oracle:
                                            C.c_void_p, C.c_void_p]
         lib.bo_rewrite_sharded.restype = C.c_size_t
         lib.bo_free.argtypes = [C.c_void_p]
+        lib.bo_set_workers.argtypes = [C.c_int, C.c_size_t]
+        lib.bo_set_workers.restype = None
+        lib.bo_set_candidate_floor.argtypes = [C.c_uint32]
+        lib.bo_set_candidate_floor.restype = None
+
+    def configure(self, workers=1, min_tokens=1 << 22, candidate_floor=64):
+        """helper threads / candidate-list shortcut of the FAST modes (the defaults are the library's)"""
+        self.lib.bo_set_workers(workers, min_tokens)
+        self.lib.bo_set_candidate_floor(candidate_floor)
 
     def train(self, data, max_merges=0, mode=FAST_CF):
         arr = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data)

@@ -34,6 +34,37 @@ def test_oracle_matches_reference_large(oracle, name, mode):
     check_against_golden(oracle, name, mode)
 
 
+@pytest.mark.parametrize("name", ["rt20k", "rt64k", "edge19661_first", "kat_k7", "testing_txt"])
+def test_helper_threads_and_candidate_list_keep_the_reference_results(oracle, name):
+    """The offline full-size fixtures (tools/make_full_golden.py) are made with the oracle's two whole-array loops split
+    over helper threads and with the maximum taken over a candidate list; both must leave every result as it is."""
+    try:
+        for workers, floor in ((4, 8),) if name == "rt64k" else ((3, 1), (1, 1)):
+            oracle.configure(workers=workers, min_tokens=0, candidate_floor=floor)
+            for mode in (FAST_CF,) if name == "rt64k" else (FAST, FAST_CF):
+                check_against_golden(oracle, name, mode)
+    finally:
+        oracle.configure()
+
+
+def test_helper_threads_on_runs_of_one_token(oracle):
+    """a == b merges: where a helper's share starts depends on the parity of the run that reaches into it.  Compared with
+    the plain single-threaded whole-map scan (which the reference fixtures pin)."""
+    rng = np.random.default_rng(20260)
+    inputs = [np.full(4001, 97, np.uint8), np.frombuffer(b"aaab" * 2500 + b"aaaaa", dtype=np.uint8)]
+    inputs += [rng.integers(97, 97 + k, size=int(rng.integers(9, 6000)), dtype=np.uint8) for k in (1, 2, 2, 3, 5)]
+    try:
+        for data in inputs:
+            oracle.configure(workers=1, candidate_floor=0)
+            rc0, m0, t0, st0 = oracle.train(data, 0, FAST_CF)
+            for workers, floor in ((2, 1), (7, 3), (64, 1)):
+                oracle.configure(workers=workers, min_tokens=0, candidate_floor=floor)
+                rc1, m1, t1, st1 = oracle.train(data, 0, FAST_CF)
+                assert rc0 == rc1 == 0 and np.array_equal(m0, m1) and np.array_equal(t0, t1) and st0 == st1
+    finally:
+        oracle.configure()
+
+
 def test_murmur_and_bucket_counts(oracle):
     # hash_table.c:8-53 on an 8-byte key; value cross-checked with an independent Python murmur3_32
     def mm3(a, b):

@@ -5,7 +5,11 @@ the 1 GB corpus.
 
   python tools/make_full_golden.py c1_exhaustion                       # random_text.txt to exhaustion (config 1)
   python tools/make_full_golden.py c3_full 1000000000 4321 32000 1     # name, bytes, seed, merges, kind (1 = zipf_bytes)
+
+BO_WORKERS=n (default: all cores) splits the oracle's two whole-array loops over helper threads (same results,
+tests/test_oracle.py); the 1 GB corpus then takes about an hour instead of most of a day.
 """
+import ctypes
 import gzip
 import hashlib
 import json
@@ -41,13 +45,17 @@ def main():
         merges = int(sys.argv[2]) if len(sys.argv) > 2 else 0
         corpus = {"kind": "file", "file": "tests/golden/random_text.txt.gz", "bytes": int(buf.size)}
     t0 = time.time()
-    rc, m, ids, st = oracle_api.load().train(buf, merges, oracle_api.FAST_CF)
+    orc = oracle_api.load()
+    workers = int(os.environ.get("BO_WORKERS", os.cpu_count() or 1))
+    orc.lib.bo_set_workers.argtypes = [ctypes.c_int, ctypes.c_size_t]
+    orc.lib.bo_set_workers(workers, 1 << 22)
+    rc, m, ids, st = orc.train(buf, merges, oracle_api.FAST_CF)
     assert rc == 0
     out = {"corpus": corpus, "cap": merges, "merges": int(len(m)), "n_ids": int(len(ids)), "merges_sha256": sha(m),
            "ids_sha256": sha(ids), "same_bucket_ties": int(st["same_bucket_ties"]),
            "threshold_edges": int(st["threshold_edges"]), "final_distinct": int(st["final_distinct"]),
            "thread_buckets": [int(x) for x in st["thread_buckets"]],
-           "made_by": "tools/make_full_golden.py (oracle FAST_CF mode)", "oracle_seconds": round(time.time() - t0, 1)}
+           "made_by": f"tools/make_full_golden.py (oracle FAST_CF mode, {workers} helper threads)", "oracle_seconds": round(time.time() - t0, 1)}
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "full", name + "_merges.npz"), merges=m.astype(np.uint32))
     with open(os.path.join(ROOT, "tests", "golden", name + ".json"), "w") as f:
         json.dump(out, f, indent=1)
