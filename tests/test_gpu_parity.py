@@ -447,6 +447,26 @@ def test_config3_first_4000_merges_match_the_oracle_digest(engine):
     assert st["batch_merges"] > 0
 
 
+def test_config3_all_32000_merges_match_the_oracle(engine):
+    """BASELINE config 3 in full: 1 GB of Zipf bytes, 32,000 merges.  The oracle's merge list and the digest of its
+    293 M ids are committed (tests/golden/c3_full.json + full/c3_full_merges.npz, made offline by
+    tools/make_full_golden.py with the oracle's helper threads); every pass of the run is behind them - the table grows
+    to tens of millions of pairs through several rehashes, ids pass the 8,192-entry class table four times over."""
+    g = _full_golden("c3_full")
+    data = corpus(1, g["corpus"]["bytes"], g["corpus"]["seed"])
+    ctx = engine.Context(0)
+    try:
+        ctx.upload(data)
+        st = ctx.train(g["cap"])
+        m, t = ctx.download()
+    finally:
+        ctx.close()
+    exp = {"merges": g["merge_list"], "n_ids": g["n_ids"], "ids_sha256": g["ids_sha256"], "same_bucket_ties": g["same_bucket_ties"],
+           "threshold_edges": g["threshold_edges"], "thread_buckets": g["thread_buckets"]}
+    check_result(exp, m, t, st, 1, "config 3, all 32,000 merges")
+    assert st["final_distinct"] == g["final_distinct"] and st["batch_merges"] > 0
+
+
 # ---- decode (SURVEY.md §8f rank 2): ids -> bytes, the inverse of the path ------------------------
 @pytest.mark.parametrize("kind,size,cap", [(0, 300_000, 600), (1, 200_000, 300), (2, 150_000, 200)])
 def test_decode_matches_oracle_and_round_trips(engine, oracle, kind, size, cap):
