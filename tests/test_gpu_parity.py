@@ -467,6 +467,22 @@ def test_config3_all_32000_merges_match_the_oracle(engine):
     assert st["final_distinct"] == g["final_distinct"] and st["batch_merges"] > 0
 
 
+def test_config5_first_chunk_50000_merges_match_the_oracle(engine):
+    """BASELINE config 5's vocabulary size on the first 125 MB chunk of its corpus (zipf_bytes seed 8888): 50,000 merges
+    (GPT-2 scale: ids up to 50,255, delta vectors of 12 x 4 x 50 k counters, the class table aliased six times over).
+    The 8 GB corpus itself is beyond the oracle's memory; its merge list for the chunk is committed
+    (tests/golden/c5_chunk0_50k.json + full/, 16 minutes of oracle time)."""
+    g = _full_golden("c5_chunk0_50k")
+    data = corpus(1, g["corpus"]["bytes"], g["corpus"]["seed"])
+    m, t, st = engine.train(data, max_merges=g["cap"])
+    exp = {"merges": g["merge_list"], "n_ids": g["n_ids"], "ids_sha256": g["ids_sha256"], "same_bucket_ties": g["same_bucket_ties"],
+           "threshold_edges": g["threshold_edges"], "thread_buckets": g["thread_buckets"]}
+    check_result(exp, m, t, st, 1, "config 5, first chunk, 50,000 merges")
+    assert st["final_distinct"] == g["final_distinct"] and st["batch_merges"] > 0
+    enc, _ = engine.encode(data, m)                   # the 50,000-rank table through the encoder: the training ids again
+    assert len(enc) == g["n_ids"] and sha(enc) == g["ids_sha256"]
+
+
 # ---- decode (SURVEY.md §8f rank 2): ids -> bytes, the inverse of the path ------------------------
 @pytest.mark.parametrize("kind,size,cap", [(0, 300_000, 600), (1, 200_000, 300), (2, 150_000, 200)])
 def test_decode_matches_oracle_and_round_trips(engine, oracle, kind, size, cap):
