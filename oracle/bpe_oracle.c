@@ -480,19 +480,6 @@ static uint64_t hset_put(hset_t *s, uint64_t key, uint32_t h, int *fresh)
     }
 }
 
-static int64_t hset_get(const hset_t *s, uint64_t key, uint32_t h)
-{
-    uint64_t p = ((uint64_t)h * 0x9E3779B97F4A7C15ull >> 20) & (s->cap - 1);
-    for (;;)
-    {
-        if (s->stamp[p] != s->epoch)
-            return -1;
-        if (s->key[p] == key)
-            return (int64_t)p;
-        p = (p + 1) & (s->cap - 1);
-    }
-}
-
 /* ------------------------------------------------------------------------------------------ */
 typedef struct
 {

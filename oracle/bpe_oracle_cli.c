@@ -2,6 +2,7 @@
  * TEST INFRASTRUCTURE — command-line front end of the CPU oracle (bpe_oracle.c).
  *   bpe_oracle_cli train  <input> <cap|0> <mode 0|1|2> <out-prefix>
  *   bpe_oracle_cli encode <input> <merges-file> <out-prefix>
+ * Environment: BO_WORKERS, BO_CAND_FLOOR select the helper-thread / candidate-list variants of the FAST modes.
  * Output files use the reference's on-disk record (bpe.c:243-339): LE {u32 a,u32 b} per merge
  * from id 256, and LE u32 per token.
  */
@@ -51,6 +52,11 @@ static int dump(const char *prefix, const char *ext, const void *p, size_t bytes
 
 int main(int argc, char **argv)
 {
+    /* BO_WORKERS=n: helper threads on every stream length; BO_CAND_FLOOR=c: candidate-list threshold (bpe_oracle.h) */
+    if (getenv("BO_WORKERS"))
+        bo_set_workers(atoi(getenv("BO_WORKERS")), 0);
+    if (getenv("BO_CAND_FLOOR"))
+        bo_set_candidate_floor((uint32_t)strtoul(getenv("BO_CAND_FLOOR"), NULL, 10));
     if (argc >= 6 && !strcmp(argv[1], "train"))
     {
         size_t n;

@@ -63,8 +63,12 @@ def main():
             data.tofile(p)
             r = run([REF, p, "0", os.path.join(d, "ref")])
             ref_ok = r.returncode == 0
-            for mode in (0, 1, 2):
-                o = run([ORA, "train", p, "0", str(mode), os.path.join(d, f"o{mode}")])
+            # modes 0-2 as they are; 3 = mode 2 with helper threads and the candidate-list argmax (what the offline
+            # full-size fixtures are made with)
+            for mode in (0, 1, 2, 3):
+                env = dict(os.environ, BO_WORKERS="3", BO_CAND_FLOOR="1") if mode == 3 else None
+                o = subprocess.run([ORA, "train", p, "0", str(min(mode, 2)), os.path.join(d, f"o{mode}")], capture_output=True,
+                                   text=True, env=env)
                 if (o.returncode == 0) != ref_ok:
                     print(f"case {c} mode {mode}: status differs ref={r.returncode} oracle={o.returncode}")
                     bad += 1
