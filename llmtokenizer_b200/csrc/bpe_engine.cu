@@ -1204,7 +1204,7 @@ static int init_state(bpe_cuda_ctx *c, u64 n_local, u64 max_merges, bool encode,
         s.rcnt[i] = c->d_rcnt[i];
         s.redge[i] = c->d_redge[i];
     }
-    s.pad_ctl = getenv("BPE_CUDA_FAKE_EXCL") ? (u32)atoi(getenv("BPE_CUDA_FAKE_EXCL")) : 0u;
+    s.pad_ctl = 0u;
     (void)encode;
     CU(cudaMemcpyAsync(c->d_st, &s, sizeof s, cudaMemcpyHostToDevice, c->stream));
     return 0;
