@@ -25,6 +25,26 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/bpe_cuda.h but not exported"
 
 
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """The boundary is a C ABI: include/bpe_cuda.h must compile as strict C99 (what the reference's bpe.c would include)
+    and as C++ (extern "C"), with no torch / CUDA types in any signature, and link against the library."""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    src = tmp_path / "use.c"
+    src.write_text('#include "bpe_cuda.h"\n'
+                   "int main(void) { bpe_pair_t p = {1u, 2u}; bpe_cuda_stats_t st; (void)p; (void)st;\n"
+                   "  return bpe_cuda_device_count() < 0 || bpe_cuda_last_error() == 0; }\n")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", str(src)])
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", inc, "-x", "c++", "-fsyntax-only", str(src)])
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(inc, "bpe_cuda.h")).read(), flags=re.S)
+    assert not re.search(r"torch|at::|cudaStream_t|__global__|#include\s*<cuda", text)
+    exe = tmp_path / "use"
+    pkg = os.path.join(ROOT, "llmtokenizer_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-I", inc, "-o", str(exe), str(src), "-L", pkg, "-lbpe_cuda", f"-Wl,-rpath,{pkg}"])
+    r = subprocess.run([str(exe)], capture_output=True)
+    assert r.returncode in (0, 1)          # runs and returns (no device here: count 0, error string present)
+
+
 def test_no_cpu_fallback_without_device():
     import llmtokenizer_b200 as L
     from llmtokenizer_b200 import _lib
