@@ -483,22 +483,6 @@ def test_config5_first_chunk_50000_merges_match_the_oracle(engine):
     assert len(enc) == g["n_ids"] and sha(enc) == g["ids_sha256"]
 
 
-def test_config4_first_chunk_encoded_with_config3s_table(engine):
-    """BASELINE config 4's shape: a chunk of ITS corpus (zipf_bytes sampling seed 777, config 3's word list) encoded with
-    the 32,000-merge table learned from config 3's corpus - a foreign table, so some ranks never occur.  The oracle's
-    rank-by-rank rewrite (bpe.c:760-772 per rank) of the 125 MB chunk took 34 minutes; the digest of its 36.7 M ids is
-    committed (tests/golden/c4_chunk0_encode.json, tools/make_encode_golden.py)."""
-    import json
-    import os
-    here = os.path.dirname(__file__)
-    g = json.load(open(os.path.join(here, "golden", "c4_chunk0_encode.json")))
-    merges = np.load(os.path.join(here, "golden", "full", "c3_full_merges.npz"))["merges"]
-    assert len(merges) == g["ranks"]
-    data = corpus(1, g["corpus"]["bytes"], g["corpus"]["seed"])
-    ids, st = engine.encode(data, merges)
-    assert len(ids) == g["n_ids"] and sha(ids) == g["ids_sha256"], st
-
-
 # ---- decode (SURVEY.md §8f rank 2): ids -> bytes, the inverse of the path ------------------------
 @pytest.mark.parametrize("kind,size,cap", [(0, 300_000, 600), (1, 200_000, 300), (2, 150_000, 200)])
 def test_decode_matches_oracle_and_round_trips(engine, oracle, kind, size, cap):
@@ -574,3 +558,19 @@ def test_zipf_bytes_200mb_10000_merges_match_the_oracle_digest(engine):
     sha = lambda a: hashlib.sha256(np.ascontiguousarray(a, dtype="<u4").tobytes()).hexdigest()
     assert len(t) == g["n_ids"] and sha(m) == g["merges_sha256"] and sha(t) == g["ids_sha256"], st
     assert st["batch_merges"] > 0
+
+
+def test_config4_first_chunk_encoded_with_config3s_table(engine):
+    """BASELINE config 4's shape: a chunk of ITS corpus (zipf_bytes sampling seed 777, config 3's word list) encoded with
+    the 32,000-merge table learned from config 3's corpus - a foreign table, so some ranks never occur.  The oracle's
+    rank-by-rank rewrite (bpe.c:760-772 per rank) of the 125 MB chunk took 34 minutes; the digest of its 36.7 M ids is
+    committed (tests/golden/c4_chunk0_encode.json, tools/make_encode_golden.py)."""
+    import json
+    import os
+    here = os.path.dirname(__file__)
+    g = json.load(open(os.path.join(here, "golden", "c4_chunk0_encode.json")))
+    merges = np.load(os.path.join(here, "golden", "full", "c3_full_merges.npz"))["merges"]
+    assert len(merges) == g["ranks"]
+    data = corpus(1, g["corpus"]["bytes"], g["corpus"]["seed"])
+    ids, st = engine.encode(data, merges)
+    assert len(ids) == g["n_ids"] and sha(ids) == g["ids_sha256"], st
